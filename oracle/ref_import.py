@@ -1,0 +1,80 @@
+"""Import the UNMODIFIED reference encoder from /root/reference (container only).
+
+TEST INFRASTRUCTURE. Nothing under ``camouflaged_vlm_b200/`` may import this file.
+``/root/reference`` does not exist on the GPU box, so only ``oracle/make_golden.py``
+and the ``-m "not gpu"`` tests that are skipped when the tree is absent use it.
+
+``import models`` fails in this image (mmcv / open_clip / dassl are missing), but
+``models/mmseg/models/sam/image_encoder.py`` only needs torch and ``.common``
+(image_encoder.py:7-22).  We therefore register an empty stub package whose
+``__path__`` points at the reference directory and load the two files below it.
+Nothing is copied; the sources stay where they lie.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("CVLM_REFERENCE_ROOT", "/root/reference")
+SAM_DIR = os.path.join(REF_ROOT, "models", "mmseg", "models", "sam")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(SAM_DIR, "image_encoder.py"))
+
+
+def _load(name: str):
+    full = f"refsam.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, os.path.join(SAM_DIR, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference_modules():
+    """Returns (image_encoder_module, common_module) of the reference."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REF_ROOT}")
+    if "refsam" not in sys.modules:
+        pkg = types.ModuleType("refsam")
+        pkg.__path__ = [SAM_DIR]
+        sys.modules["refsam"] = pkg
+    common = _load("common")
+    enc = _load("image_encoder")
+    return enc, common
+
+
+def load_reference_decoder_modules():
+    """mask_decoder_edge.py + transformer_maskdecoder_edge.py (only need .common)."""
+    load_reference_modules()
+    return _load("mask_decoder_edge"), _load("transformer_maskdecoder_edge")
+
+
+def build_reference_encoder(cfg):
+    """Instantiate the reference ImageEncoderViT the way models/sam_maskdecoder_edge.py:119-135 does."""
+    from functools import partial
+
+    import torch
+
+    enc, _ = load_reference_modules()
+    return enc.ImageEncoderViT(
+        img_size=cfg.img_size,
+        patch_size=cfg.patch_size,
+        in_chans=cfg.in_chans,
+        embed_dim=cfg.embed_dim,
+        depth=cfg.depth,
+        num_heads=cfg.num_heads,
+        mlp_ratio=cfg.mlp_ratio,
+        out_chans=cfg.out_chans,
+        qkv_bias=cfg.qkv_bias,
+        norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+        act_layer=torch.nn.GELU,
+        use_abs_pos=cfg.use_abs_pos,
+        use_rel_pos=cfg.use_rel_pos,
+        rel_pos_zero_init=True,
+        window_size=cfg.window_size,
+        global_attn_indexes=tuple(cfg.global_attn_indexes),
+    )
