@@ -1,0 +1,66 @@
+// Internal declarations shared by the kernels, the op-level C-ABI and the encoder runtime.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cvlm.h"
+
+namespace cvlm {
+
+int set_error(int code, const char* fmt, ...);
+
+#define CVLM_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::cvlm::set_error(CVLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                     __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define CVLM_TRY(expr)              \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != CVLM_OK) return _rc; \
+    } while (0)
+
+// ---- GEMM (gemm_tcgen05.cu):  out = epilogue(A1 * B1^T [+ A2 * B2^T])
+struct GemmArgs {
+    const void* a1 = nullptr;  long long lda1 = 0;   // bf16 [M, K1], row stride lda1 elements
+    const void* b1 = nullptr;  long long ldb1 = 0;   // bf16 [Nb, K1] (Nb <= N rows actually stored)
+    int k1 = 0;
+    const void* a2 = nullptr;  long long lda2 = 0;   // optional second K segment
+    const void* b2 = nullptr;  long long ldb2 = 0;
+    int k2 = 0;
+    int m = 0, n = 0;          // logical output shape
+    int b_rows = 0;            // rows present in B1/B2 (0 -> n); rows beyond read as zero
+    const float* bias = nullptr;       // [n] or null
+    const float* residual = nullptr;   // fp32 [*, ldr] or null
+    long long ldr = 0;
+    int res_row_mod = 0;       // >0: residual row = row % res_row_mod (pos_embed broadcast)
+    void* out = nullptr;       // fp32 or bf16 [M, ldo]
+    long long ldo = 0;
+    int out_bf16 = 0;
+    int act_gelu = 0;
+};
+int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+// ---- attention (attention.cu)
+int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
+                     int window, int heads, int head_dim, cudaStream_t stream);
+
+// ---- row kernels (rowops.cu)
+int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
+                     int cols, float eps, cudaStream_t stream);
+int cast_bf16_launch(const float* x, void* out, long long n, cudaStream_t stream);
+int im2col_patch_launch(const float* img, void* out, int batch, int chans, int img_size, int patch,
+                        cudaStream_t stream);
+int im2col_3x3_launch(const void* x_nhwc_bf16, void* out, int batch, int grid_side, int chans, cudaStream_t stream);
+int layernorm_nchw_out_launch(const float* x, const float* gamma, const float* beta, float* out_nchw, int batch,
+                              int tokens, int chans, float eps, cudaStream_t stream);
+int adapter_embed_launch(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,
+                         int batch, int tokens, int dim, int rank, int rank_pad, cudaStream_t stream);
+
+}  // namespace cvlm

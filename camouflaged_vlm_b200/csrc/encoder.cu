@@ -1,0 +1,491 @@
+// Encoder runtime: the C-ABI (include/cvlm.h) and the launch schedule of ImageEncoderViT.forward
+// (image_encoder.py:132-155) over the kernels in gemm_tcgen05.cu / attention.cu / rowops.cu.
+//
+// Data layout in HBM for a batch of B images (M = B * T tokens, T = g*g, D = embed_dim):
+//   x     fp32 [M, D]      residual stream (NHWC), updated in place by the proj / lin2 epilogues
+//   a     bf16 [M, D]      LayerNorm output, then attention output, then LayerNorm output again
+//   big   bf16 [M, 4D]     qkv (3D) / MLP hidden (4D) / im2col patches / neck im2col (they never coexist)
+//   hand  fp32 [M, RP]     PatchEmbed2 of the high-passed image
+//   t     bf16 [M, RP]     hand + embedding (adapter input)
+//   gall  bf16 [M, depth*RP]  GELU(lightweight_mlp_i(t)) for all i; prompt_i = gall_i * W_shared^T + b
+// The 32 prompt tensors the reference materialises (32 x [B,4096,1280] fp32) never exist: prompt_{i+1}
+// is a second K segment (K = RP) of block i's lin2 GEMM.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "cvlm_internal.cuh"
+
+namespace cvlm {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct TensorRef {
+    const void* ptr;
+    long long nbytes;
+};
+
+}  // namespace cvlm
+
+struct ProfSpan {
+    int kind;
+    cudaEvent_t start, stop;
+};
+
+struct cvlm_encoder {
+    cvlm_encoder_config cfg;
+    std::unordered_map<std::string, cvlm::TensorRef> tensors;
+    long long last_launches = 0;
+    bool profiling = false;
+    std::vector<ProfSpan> spans;        // spans of the profiled forwards since the last get_profile
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace cvlm {
+
+enum ProfKind {
+    K_GEMM_QKV = 0, K_GEMM_PROJ, K_GEMM_LIN1, K_GEMM_LIN2, K_GEMM_OTHER, K_ATTN_WINDOW, K_ATTN_GLOBAL, K_LAYERNORM,
+    K_OTHER, K_COUNT
+};
+static_assert(K_COUNT == CVLM_PROF_KINDS, "cvlm.h CVLM_PROF_KINDS out of sync");
+
+static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    long long off_x, off_a, off_big, off_hand, off_t, off_gall, total;
+    long long big_cols;
+};
+
+static Workspace plan_workspace(const cvlm_encoder_config& c, int batch) {
+    const long long g = c.img_size / c.patch_size, T = g * g, M = T * batch;
+    const long long D = c.embed_dim, OC = c.out_chans, RP = c.rank_pad;
+    const long long kp = static_cast<long long>(c.in_chans) * c.patch_size * c.patch_size;
+    Workspace w;
+    long long big_cols = c.mlp_dim;
+    if (3 * D > big_cols) big_cols = 3 * D;
+    if (2 * kp > big_cols) big_cols = 2 * kp;
+    if (9 * OC > big_cols) big_cols = 9 * OC;
+    w.big_cols = big_cols;
+    long long off = 0;
+    const long long x_bytes = M * (D * 4 > 2 * OC * 4 ? D * 4 : 2 * OC * 4);
+    const long long a_bytes = M * (D > OC ? D : OC) * 2;
+    w.off_x = off;     off = align_up(off + x_bytes, 1024);
+    w.off_a = off;     off = align_up(off + a_bytes, 1024);
+    w.off_big = off;   off = align_up(off + M * big_cols * 2, 1024);
+    w.off_hand = off;  off = align_up(off + M * RP * 4, 1024);
+    w.off_t = off;     off = align_up(off + M * RP * 2, 1024);
+    w.off_gall = off;  off = align_up(off + M * c.depth * RP * 2, 1024);
+    w.total = off;
+    return w;
+}
+
+struct Fwd {
+    cvlm_encoder* enc;
+    cudaStream_t stream;
+    long long launches = 0;
+    char namebuf[96];
+
+    int get(const char* name, long long expect_bytes, const void** out) {
+        auto it = enc->tensors.find(name);
+        if (it == enc->tensors.end()) return set_error(CVLM_ERR_MISSING, "tensor '%s' was not registered", name);
+        if (expect_bytes > 0 && it->second.nbytes != expect_bytes)
+            return set_error(CVLM_ERR_MISSING, "tensor '%s' has %lld bytes, expected %lld", name, it->second.nbytes,
+                             expect_bytes);
+        *out = it->second.ptr;
+        return CVLM_OK;
+    }
+    int getb(int blk, const char* suffix, long long expect_bytes, const void** out) {
+        snprintf(namebuf, sizeof(namebuf), "blk.%d.%s", blk, suffix);
+        return get(namebuf, expect_bytes, out);
+    }
+    cudaEvent_t event() {
+        if (!enc->event_pool.empty()) {
+            cudaEvent_t e = enc->event_pool.back();
+            enc->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    // every kernel launch of the forward goes through here: counts it and, when profiling is on,
+    // brackets it with CUDA events on the launching stream
+    template <typename F>
+    int run(int kind, F&& launch) {
+        ++launches;
+        if (!enc->profiling) return launch();
+        ProfSpan sp{kind, event(), event()};
+        cudaEventRecord(sp.start, stream);
+        const int rc = launch();
+        cudaEventRecord(sp.stop, stream);
+        enc->spans.push_back(sp);
+        return rc;
+    }
+    int gemm(int kind, const GemmArgs& a) {
+        return run(kind, [&] { return gemm_launch(a, stream); });
+    }
+};
+
+static int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
+                        float* const* interm, int stop_after_block, float* x_out, void* workspace,
+                        long long workspace_bytes, cudaStream_t stream) {
+    if (!enc || !images || !highpass || !workspace) return set_error(CVLM_ERR_ARG, "forward: null argument");
+    if (batch <= 0) return set_error(CVLM_ERR_ARG, "forward: batch must be positive");
+    const cvlm_encoder_config& c = enc->cfg;
+    const Workspace ws = plan_workspace(c, batch);
+    if (workspace_bytes < ws.total)
+        return set_error(CVLM_ERR_WORKSPACE, "workspace has %lld bytes, need %lld", workspace_bytes, ws.total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(CVLM_ERR_ARG, "workspace must be 256-byte aligned");
+
+    const int g = c.img_size / c.patch_size, T = g * g, D = c.embed_dim, OC = c.out_chans, RP = c.rank_pad;
+    const int hd = D / c.num_heads, depth = c.depth, kp = c.in_chans * c.patch_size * c.patch_size;
+    const long long M = static_cast<long long>(T) * batch;
+    if (M > 0x7fffffffLL / 2) return set_error(CVLM_ERR_UNSUPPORTED, "forward: batch too large for one call; split it");
+    char* wsb = static_cast<char*>(workspace);
+    float* x = reinterpret_cast<float*>(wsb + ws.off_x);
+    __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_a);
+    __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_big);
+    float* hand = reinterpret_cast<float*>(wsb + ws.off_hand);
+    __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_t);
+    __nv_bfloat16* gall = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_gall);
+    const long long ldg = static_cast<long long>(depth) * RP;
+
+    Fwd f{enc, stream};
+    const void *patch_w, *patch_b, *pos = nullptr, *hand_w, *hand_b, *emb_wt, *emb_cst, *lw_w, *lw_b, *sh_w, *sh_b;
+    CVLM_TRY(f.get("patch.w", 2LL * D * kp, &patch_w));
+    CVLM_TRY(f.get("patch.b", 4LL * D, &patch_b));
+    if (c.use_abs_pos) CVLM_TRY(f.get("pos", 4LL * T * D, &pos));
+    CVLM_TRY(f.get("hand.w", 2LL * c.rank * kp, &hand_w));
+    CVLM_TRY(f.get("hand.b", 4LL * RP, &hand_b));
+    CVLM_TRY(f.get("emb.wt", 4LL * D * RP, &emb_wt));
+    CVLM_TRY(f.get("emb.cst", 4LL * T * RP, &emb_cst));
+    CVLM_TRY(f.get("lw.w", 2LL * depth * RP * RP, &lw_w));
+    CVLM_TRY(f.get("lw.b", 4LL * depth * RP, &lw_b));
+    CVLM_TRY(f.get("shared.w", 2LL * D * RP, &sh_w));
+    CVLM_TRY(f.get("shared.b", 4LL * D, &sh_b));
+
+    // ------------------------------------------------------------------ stem
+    __nv_bfloat16* patches = big;
+    __nv_bfloat16* patches_hp = big + M * kp;
+    CVLM_TRY(f.run(K_OTHER, [&] { return im2col_patch_launch(images, patches, batch, c.in_chans, c.img_size, c.patch_size, stream); }));
+    CVLM_TRY(f.run(K_OTHER, [&] { return im2col_patch_launch(highpass, patches_hp, batch, c.in_chans, c.img_size, c.patch_size, stream); }));
+    {   // PatchEmbed (:655-659) + pos_embed (:139-140): x = patches * Wp^T + bp + pos[row % T]
+        GemmArgs ga;
+        ga.a1 = patches; ga.lda1 = kp; ga.b1 = patch_w; ga.ldb1 = kp; ga.k1 = kp;
+        ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(patch_b);
+        ga.residual = static_cast<const float*>(pos); ga.ldr = D; ga.res_row_mod = T;
+        ga.out = x; ga.ldo = D;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    {   // PatchEmbed2 of the high-passed image (:283-285): hand = patches_hp * Wh^T + bh   (fp32 [M, RP])
+        GemmArgs ga;
+        ga.a1 = patches_hp; ga.lda1 = kp; ga.b1 = hand_w; ga.ldb1 = kp; ga.k1 = kp;
+        ga.m = static_cast<int>(M); ga.n = RP; ga.b_rows = c.rank; ga.bias = static_cast<const float*>(hand_b);
+        ga.out = hand; ga.ldo = RP;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    CVLM_TRY(f.run(K_OTHER, [&] {
+        return adapter_embed_launch(x, hand, static_cast<const float*>(emb_wt), static_cast<const float*>(emb_cst), t,
+                                    batch, T, D, c.rank, RP, stream);
+    }));
+    {   // all 32 lightweight MLPs at once (:291-293): gall = GELU(t * Wlw^T + blw)   (bf16 [M, depth*RP])
+        GemmArgs ga;
+        ga.a1 = t; ga.lda1 = RP; ga.b1 = lw_w; ga.ldb1 = RP; ga.k1 = RP;
+        ga.m = static_cast<int>(M); ga.n = static_cast<int>(ldg); ga.bias = static_cast<const float*>(lw_b);
+        ga.out = gall; ga.ldo = ldg; ga.out_bf16 = 1; ga.act_gelu = 1;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    auto prompt_add = [&](int blk, const float* src, float* dst) -> int {
+        // dst = src + gall_blk * Wshared^T + bshared    (shared_mlp :294, add :145)
+        GemmArgs ga;
+        ga.a1 = gall + static_cast<long long>(blk) * RP; ga.lda1 = ldg; ga.b1 = sh_w; ga.ldb1 = RP; ga.k1 = RP;
+        ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(sh_b);
+        ga.residual = src; ga.ldr = D; ga.out = dst; ga.ldo = D;
+        return f.gemm(K_GEMM_OTHER, ga);
+    };
+    CVLM_TRY(prompt_add(0, x, x));
+
+    auto finish_partial = [&](const float* src) -> int {
+        CVLM_CUDA(cudaMemcpyAsync(x_out, src, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+        enc->last_launches = f.launches;
+        return CVLM_OK;
+    };
+    if (x_out && stop_after_block < 0) return finish_partial(x);
+
+    // ------------------------------------------------------------------ blocks (Block.forward :430-446)
+    float* xcur = x;
+    int interm_idx = 0;
+    for (int i = 0; i < depth; ++i) {
+        const int window = c.is_global[i] ? 0 : c.window_size;
+        const int S = window > 0 ? window : g;
+        const long long relb = 2LL * (2 * S - 1) * hd;
+        const void *ln1w, *ln1b, *qkv_w, *qkv_b, *relh, *relw, *proj_w, *proj_b, *ln2w, *ln2b, *l1w, *l1b, *l2w, *l2b,
+            *l2bf = nullptr;
+        CVLM_TRY(f.getb(i, "ln1.w", 4LL * D, &ln1w));
+        CVLM_TRY(f.getb(i, "ln1.b", 4LL * D, &ln1b));
+        CVLM_TRY(f.getb(i, "qkv.w", 2LL * 3 * D * D, &qkv_w));
+        CVLM_TRY(f.getb(i, "qkv.b", 4LL * 3 * D, &qkv_b));
+        CVLM_TRY(f.getb(i, "relh", relb, &relh));
+        CVLM_TRY(f.getb(i, "relw", relb, &relw));
+        CVLM_TRY(f.getb(i, "proj.w", 2LL * D * D, &proj_w));
+        CVLM_TRY(f.getb(i, "proj.b", 4LL * D, &proj_b));
+        CVLM_TRY(f.getb(i, "ln2.w", 4LL * D, &ln2w));
+        CVLM_TRY(f.getb(i, "ln2.b", 4LL * D, &ln2b));
+        CVLM_TRY(f.getb(i, "lin1.w", 2LL * c.mlp_dim * D, &l1w));
+        CVLM_TRY(f.getb(i, "lin1.b", 4LL * c.mlp_dim, &l1b));
+        CVLM_TRY(f.getb(i, "lin2.w", 2LL * D * c.mlp_dim, &l2w));
+        CVLM_TRY(f.getb(i, "lin2.b", 4LL * D, &l2b));
+        if (i + 1 < depth) CVLM_TRY(f.getb(i, "lin2.bf", 4LL * D, &l2bf));
+
+        CVLM_TRY(f.run(K_LAYERNORM, [&] {
+            return layernorm_launch(xcur, static_cast<const float*>(ln1w), static_cast<const float*>(ln1b), a, 1, M, D,
+                                    c.ln_eps, stream);
+        }));
+        {   // qkv (:491); bias = [b_q, 0, 0]
+            GemmArgs ga;
+            ga.a1 = a; ga.lda1 = D; ga.b1 = qkv_w; ga.ldb1 = D; ga.k1 = D;
+            ga.m = static_cast<int>(M); ga.n = 3 * D; ga.bias = static_cast<const float*>(qkv_b);
+            ga.out = big; ga.ldo = 3 * D; ga.out_bf16 = 1;
+            CVLM_TRY(f.gemm(K_GEMM_QKV, ga));
+        }
+        CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
+            return attention_launch(big, a, relh, relw, batch, g, window, c.num_heads, hd, stream);
+        }));
+        {   // proj (:502) + shortcut (:443); bias = b_proj + W_proj * b_v
+            GemmArgs ga;
+            ga.a1 = a; ga.lda1 = D; ga.b1 = proj_w; ga.ldb1 = D; ga.k1 = D;
+            ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(proj_b);
+            ga.residual = xcur; ga.ldr = D; ga.out = xcur; ga.ldo = D;
+            CVLM_TRY(f.gemm(K_GEMM_PROJ, ga));
+        }
+        CVLM_TRY(f.run(K_LAYERNORM, [&] {
+            return layernorm_launch(xcur, static_cast<const float*>(ln2w), static_cast<const float*>(ln2b), a, 1, M, D,
+                                    c.ln_eps, stream);
+        }));
+        {   // lin1 + GELU (common.py:26)
+            GemmArgs ga;
+            ga.a1 = a; ga.lda1 = D; ga.b1 = l1w; ga.ldb1 = D; ga.k1 = D;
+            ga.m = static_cast<int>(M); ga.n = c.mlp_dim; ga.bias = static_cast<const float*>(l1b);
+            ga.out = big; ga.ldo = c.mlp_dim; ga.out_bf16 = 1; ga.act_gelu = 1;
+            CVLM_TRY(f.gemm(K_GEMM_LIN1, ga));
+        }
+        const bool want_interm = interm != nullptr && c.is_global[i];
+        const bool stop_here = x_out != nullptr && stop_after_block == i;
+        const bool last = i + 1 == depth;
+        const bool fold = !last && !want_interm && !stop_here;
+        float* dst = want_interm ? interm[interm_idx] : xcur;
+        {   // lin2 + shortcut (:444) [+ prompt_{i+1} as a second K segment when nothing needs x before it]
+            GemmArgs ga;
+            ga.a1 = big; ga.lda1 = c.mlp_dim; ga.b1 = l2w; ga.ldb1 = c.mlp_dim; ga.k1 = c.mlp_dim;
+            if (fold) {
+                ga.a2 = gall + static_cast<long long>(i + 1) * RP; ga.lda2 = ldg; ga.b2 = sh_w; ga.ldb2 = RP; ga.k2 = RP;
+            }
+            ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(fold ? l2bf : l2b);
+            ga.residual = xcur; ga.ldr = D; ga.out = dst; ga.ldo = D;
+            CVLM_TRY(f.gemm(K_GEMM_LIN2, ga));
+        }
+        if (want_interm) ++interm_idx;
+        if (stop_here) return finish_partial(dst);
+        if (!fold && !last) {
+            CVLM_TRY(prompt_add(i + 1, dst, x));
+            xcur = x;
+        } else {
+            xcur = dst;
+        }
+    }
+
+    // ------------------------------------------------------------------ neck (:98-114, :150)
+    if (!out) return set_error(CVLM_ERR_ARG, "forward: null output");
+    const void *c1w, *n1w, *n1b, *c2w, *n2w, *n2b;
+    CVLM_TRY(f.get("neck.conv1.w", 2LL * OC * D, &c1w));
+    CVLM_TRY(f.get("neck.ln1.w", 4LL * OC, &n1w));
+    CVLM_TRY(f.get("neck.ln1.b", 4LL * OC, &n1b));
+    CVLM_TRY(f.get("neck.conv2.w", 2LL * OC * 9 * OC, &c2w));
+    CVLM_TRY(f.get("neck.ln2.w", 4LL * OC, &n2w));
+    CVLM_TRY(f.get("neck.ln2.b", 4LL * OC, &n2b));
+    CVLM_TRY(f.run(K_OTHER, [&] { return cast_bf16_launch(xcur, a, M * D, stream); }));
+    // n1 / n2 live in the (now dead) x region unless the final residual stream is x itself being read...
+    // the cast above already consumed it, so the region is free either way.
+    float* n1 = x;
+    float* n2 = x + M * OC;
+    {   // 1x1 conv, no bias
+        GemmArgs ga;
+        ga.a1 = a; ga.lda1 = D; ga.b1 = c1w; ga.ldb1 = D; ga.k1 = D;
+        ga.m = static_cast<int>(M); ga.n = OC; ga.out = n1; ga.ldo = OC;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    // LayerNorm2d over channels == LayerNorm over the last dim of NHWC
+    CVLM_TRY(f.run(K_LAYERNORM, [&] {
+        return layernorm_launch(n1, static_cast<const float*>(n1w), static_cast<const float*>(n1b), a, 1, M, OC,
+                                c.ln2d_eps, stream);
+    }));
+    CVLM_TRY(f.run(K_OTHER, [&] { return im2col_3x3_launch(a, big, batch, g, OC, stream); }));
+    {   // 3x3 conv as a GEMM over the 9 taps, no bias
+        GemmArgs ga;
+        ga.a1 = big; ga.lda1 = 9LL * OC; ga.b1 = c2w; ga.ldb1 = 9LL * OC; ga.k1 = 9 * OC;
+        ga.m = static_cast<int>(M); ga.n = OC; ga.out = n2; ga.ldo = OC;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    CVLM_TRY(f.run(K_OTHER, [&] {
+        return layernorm_nchw_out_launch(n2, static_cast<const float*>(n2w), static_cast<const float*>(n2b), out, batch,
+                                         T, OC, c.ln2d_eps, stream);
+    }));
+    enc->last_launches = f.launches;
+    return CVLM_OK;
+}
+
+}  // namespace cvlm
+
+// ====================================================================================== C ABI
+using namespace cvlm;
+
+extern "C" {
+
+const char* cvlm_last_error(void) { return g_err; }
+int cvlm_abi_version(void) { return 1; }
+
+int cvlm_encoder_create(const cvlm_encoder_config* cfg, cvlm_encoder** out) {
+    if (!cfg || !out) return set_error(CVLM_ERR_ARG, "create: null argument");
+    const cvlm_encoder_config& c = *cfg;
+    if (c.patch_size != 16 || c.img_size <= 0 || c.img_size % 16)
+        return set_error(CVLM_ERR_UNSUPPORTED, "create: patch_size must be 16 and img_size a multiple of 16");
+    if (c.depth <= 0 || c.depth > CVLM_MAX_DEPTH) return set_error(CVLM_ERR_UNSUPPORTED, "create: depth out of range");
+    if (c.num_heads <= 0 || c.embed_dim % c.num_heads) return set_error(CVLM_ERR_ARG, "create: embed_dim %% num_heads != 0");
+    const int hd = c.embed_dim / c.num_heads;
+    if (hd != 64 && hd != 80) return set_error(CVLM_ERR_UNSUPPORTED, "create: head_dim %d (supported: 64, 80)", hd);
+    if (c.embed_dim % 8 || c.mlp_dim % 8 || c.out_chans % 8)
+        return set_error(CVLM_ERR_UNSUPPORTED, "create: embed_dim, mlp_dim, out_chans must be multiples of 8");
+    if (c.rank <= 0 || c.rank_pad < c.rank || c.rank_pad % 8 || c.rank_pad > 40)
+        return set_error(CVLM_ERR_UNSUPPORTED, "create: adapter rank %d / pad %d unsupported", c.rank, c.rank_pad);
+    if (c.img_size / 16 > 64) return set_error(CVLM_ERR_UNSUPPORTED, "create: token grid larger than 64x64");
+    if (c.window_size < 0) return set_error(CVLM_ERR_ARG, "create: negative window_size");
+    cvlm_encoder* e = new cvlm_encoder();
+    e->cfg = c;
+    *out = e;
+    return CVLM_OK;
+}
+
+int cvlm_encoder_destroy(cvlm_encoder* enc) {
+    if (enc) {
+        for (const ProfSpan& sp : enc->spans) {
+            cudaEventDestroy(sp.start);
+            cudaEventDestroy(sp.stop);
+        }
+        for (cudaEvent_t e : enc->event_pool) cudaEventDestroy(e);
+    }
+    delete enc;
+    return CVLM_OK;
+}
+
+int cvlm_encoder_set_tensor(cvlm_encoder* enc, const char* name, const void* dev_ptr, long long nbytes) {
+    if (!enc || !name || !dev_ptr || nbytes <= 0) return set_error(CVLM_ERR_ARG, "set_tensor: bad argument");
+    if (reinterpret_cast<uintptr_t>(dev_ptr) & 15) return set_error(CVLM_ERR_ARG, "set_tensor: '%s' is not 16-byte aligned", name);
+    enc->tensors[name] = TensorRef{dev_ptr, nbytes};
+    return CVLM_OK;
+}
+
+long long cvlm_encoder_workspace_bytes(const cvlm_encoder* enc, int batch) {
+    if (!enc || batch <= 0) return set_error(CVLM_ERR_ARG, "workspace_bytes: bad argument");
+    return plan_workspace(enc->cfg, batch).total;
+}
+
+int cvlm_encoder_forward(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
+                         float* const* interm, void* workspace, long long workspace_bytes, cvlm_stream_t stream) {
+    return forward_impl(enc, images, highpass, batch, out, interm, -1, nullptr, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const float* highpass, int batch,
+                                 int stop_after_block, float* x_out, void* workspace, long long workspace_bytes,
+                                 cvlm_stream_t stream) {
+    if (!x_out) return set_error(CVLM_ERR_ARG, "forward_partial: null x_out");
+    return forward_impl(enc, images, highpass, batch, nullptr, nullptr, stop_after_block, x_out, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+long long cvlm_encoder_last_launch_count(const cvlm_encoder* enc) { return enc ? enc->last_launches : 0; }
+
+int cvlm_encoder_set_profiling(cvlm_encoder* enc, int enable) {
+    if (!enc) return set_error(CVLM_ERR_ARG, "set_profiling: null handle");
+    enc->profiling = enable != 0;
+    return CVLM_OK;
+}
+
+int cvlm_encoder_get_profile(cvlm_encoder* enc, float* ms_by_kind, int* launches_by_kind) {
+    if (!enc || !ms_by_kind || !launches_by_kind) return set_error(CVLM_ERR_ARG, "get_profile: null argument");
+    for (int k = 0; k < K_COUNT; ++k) {
+        ms_by_kind[k] = 0.f;
+        launches_by_kind[k] = 0;
+    }
+    for (const ProfSpan& sp : enc->spans) {
+        CVLM_CUDA(cudaEventSynchronize(sp.stop));
+        float ms = 0.f;
+        CVLM_CUDA(cudaEventElapsedTime(&ms, sp.start, sp.stop));
+        ms_by_kind[sp.kind] += ms;
+        launches_by_kind[sp.kind] += 1;
+        enc->event_pool.push_back(sp.start);
+        enc->event_pool.push_back(sp.stop);
+    }
+    enc->spans.clear();
+    return CVLM_OK;
+}
+
+int cvlm_op_gemm_bf16(const void* a1, long long lda1, const void* b1, long long ldb1, int k1, const void* a2,
+                      long long lda2, const void* b2, long long ldb2, int k2, int m, int n, int b_rows,
+                      const float* bias, const float* residual, long long ldr, int res_row_mod, void* out,
+                      long long ldo, int out_bf16, int act_gelu, cvlm_stream_t stream) {
+    GemmArgs ga;
+    ga.a1 = a1; ga.lda1 = lda1; ga.b1 = b1; ga.ldb1 = ldb1; ga.k1 = k1;
+    ga.a2 = a2; ga.lda2 = lda2; ga.b2 = b2; ga.ldb2 = ldb2; ga.k2 = k2;
+    ga.m = m; ga.n = n; ga.b_rows = b_rows; ga.bias = bias; ga.residual = residual; ga.ldr = ldr;
+    ga.res_row_mod = res_row_mod; ga.out = out; ga.ldo = ldo; ga.out_bf16 = out_bf16; ga.act_gelu = act_gelu;
+    return gemm_launch(ga, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
+                      int grid_side, int window, int heads, int head_dim, cvlm_stream_t stream) {
+    return attention_launch(qkv, out, rel_pos_h, rel_pos_w, batch, grid_side, window, heads, head_dim,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
+                      int cols, float eps, cvlm_stream_t stream) {
+    return layernorm_launch(x, gamma, beta, out, out_bf16, rows, cols, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_layernorm2d_nchw(const float* x, const float* gamma, const float* beta, float* out_nchw, int batch,
+                             int tokens, int chans, float eps, cvlm_stream_t stream) {
+    return layernorm_nchw_out_launch(x, gamma, beta, out_nchw, batch, tokens, chans, eps,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_im2col_patch16(const float* img, void* out, int batch, int chans, int img_size, cvlm_stream_t stream) {
+    return im2col_patch_launch(img, out, batch, chans, img_size, 16, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_im2col_3x3(const void* x_nhwc, void* out, int batch, int grid_side, int chans, cvlm_stream_t stream) {
+    return im2col_3x3_launch(x_nhwc, out, batch, grid_side, chans, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_cast_bf16(const float* x, void* out, long long n, cvlm_stream_t stream) {
+    return cast_bf16_launch(x, out, n, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_adapter_embed(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,
+                          int batch, int tokens, int dim, int rank, int rank_pad, cvlm_stream_t stream) {
+    return adapter_embed_launch(x0, hand, w_t, cst, t_out, batch, tokens, dim, rank, rank_pad,
+                                static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

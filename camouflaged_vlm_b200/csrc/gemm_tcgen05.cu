@@ -1,0 +1,343 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A1 * B1^T [+ A2 * B2^T]).
+//
+// Carries every nn.Linear / 1x1 / im2col'd conv of the encoder:
+//   PatchEmbed.proj (image_encoder.py:651-659, + pos_embed :139-140 as a row-periodic residual),
+//   Attention.qkv / .proj (:476-477, :491, :502), MLPBlock.lin1 / lin2 (common.py:21-26, GELU and
+//   the shortcut adds of Block.forward :443-444 fused), the adapter linears (:252-259, :287-296 -- the
+//   rank-r prompt of the NEXT block rides along as a second K segment of lin2), neck convs (:98-114).
+//
+// Design: one CTA per SM, 128x256 output tile, 64-wide K blocks.
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (SWIZZLE_128B) into a 4-stage smem ring
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M128 N256 K16, bf16 -> fp32 in TMEM)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
+//   warps 4-11  epilogue: tcgen05.ld -> registers -> bias / GELU / residual -> global
+// The accumulator double buffer lets the MMA of tile i+1 overlap the epilogue of tile i.
+// Operands are K-major in global memory (activations [M,K], weights [N,K]); ragged M/N/K edges
+// are handled by TMA out-of-bounds zero fill plus predicated stores.
+#include <mutex>
+#include <unordered_map>
+
+#include "cvlm_internal.cuh"
+#include "ptx.cuh"
+
+namespace cvlm {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE = BM * BK * 2;     // 16 KB
+constexpr int B_STAGE = BN * BK * 2;     // 32 KB
+constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmEpi {
+    const float* bias;
+    const float* residual;
+    long long ldr;
+    int res_row_mod;
+    void* out;
+    long long ldo;
+    int out_bf16;
+    int act_gelu;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                         const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                         int kblocks1, int kblocks2, int M, int N, int tiles_m, int tiles_n, GemmEpi ep) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = base + STAGES * A_STAGE;
+    const uint32_t bars = sB + STAGES * B_STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = kblocks1 + kblocks2;
+    const int num_tiles = tiles_m * tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB1);
+        if (kblocks2 > 0) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), A_STAGE + B_STAGE);
+                    const bool second = kb >= kblocks1;
+                    const int kc = (second ? kb - kblocks1 : kb) * BK;
+                    tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), kc, m0);
+                    tma_load_2d(sB + stage * B_STAGE, second ? &tmB2 : &tmB1, full_bar(stage), kc, n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single lane) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                mbar_wait(tempty_bar(acc), (((iter >> 1) & 1) ^ 1u));   // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_k_sw128(sA + stage * A_STAGE);
+                    const uint64_t bdesc = umma_desc_k_sw128(sB + stage * B_STAGE);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the 128 B swizzle span: +2 in 16-byte units
+                        umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps =====================
+        const int ew = warp - 4;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
+        const int half = ew >> 2;           // which 128 of the 256 accumulator columns
+        const float* __restrict__ bias = ep.bias;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < M;
+            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+            const float* res_row = ep.residual ? ep.residual + rrow * ep.ldr : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = n0 + half * 128 + c * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128 + c * 32, v);
+                tmem_ld_wait(v);
+                if (c == 3) {
+                    // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                if (!row_ok || col0 >= N) continue;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = col0 + j;
+                    if (col >= N) break;     // N is a multiple of 8, so groups of 4 are all-or-nothing
+                    float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3]));
+                    if (bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
+                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                    }
+                    if (ep.act_gelu) {
+                        x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                    }
+                    if (res_row) {
+                        const float4 rr = *reinterpret_cast<const float4*>(res_row + col);
+                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                    }
+                    v[j] = __float_as_uint(x.x); v[j + 1] = __float_as_uint(x.y);
+                    v[j + 2] = __float_as_uint(x.z); v[j + 3] = __float_as_uint(x.w);
+                }
+                if (ep.out_bf16) {
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (col0 + j >= N) break;
+                        uint4 pk;
+                        pk.x = pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                        *reinterpret_cast<uint4*>(o + j) = pk;
+                    }
+                } else {
+                    float* o = static_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col0 + j >= N) break;
+                        *reinterpret_cast<uint4*>(o + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    long long rows, cols, ld;
+    int box_rows;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ static_cast<size_t>(k.rows);
+        h = h * 1000003u ^ static_cast<size_t>(k.cols);
+        h = h * 1000003u ^ static_cast<size_t>(k.ld);
+        h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+        return h;
+    }
+};
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = box_rows x 64, 128-byte swizzle.
+// Tensor maps only depend on (pointer, shape), so they are memoised: a forward pass re-uses ~10 maps.
+static int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
+                           int box_rows) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return CVLM_OK;
+        }
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(CVLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+        return set_error(CVLM_ERR_ARG, "gemm: operand pointer / row stride must be 16-byte aligned");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(CVLM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return CVLM_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+    if (!a.a1 || !a.b1 || !a.out) return set_error(CVLM_ERR_ARG, "gemm: null operand");
+    if (a.m <= 0 || a.n <= 0 || a.k1 <= 0) return set_error(CVLM_ERR_ARG, "gemm: bad shape m=%d n=%d k=%d", a.m, a.n, a.k1);
+    if (a.n % 8) return set_error(CVLM_ERR_ARG, "gemm: n=%d must be a multiple of 8 (pad the output)", a.n);
+    if ((a.k2 > 0) != (a.a2 != nullptr && a.b2 != nullptr)) return set_error(CVLM_ERR_ARG, "gemm: inconsistent second K segment");
+    if ((reinterpret_cast<uintptr_t>(a.out) & 15) || (a.ldo % 8) || (a.residual && ((reinterpret_cast<uintptr_t>(a.residual) & 15) || (a.ldr % 4))) ||
+        (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)))
+        return set_error(CVLM_ERR_ARG, "gemm: epilogue pointers / strides must allow 16-byte vectors");
+    const int brows = a.b_rows > 0 ? a.b_rows : a.n;
+    CUtensorMap tA1, tB1, tA2, tB2;
+    CVLM_TRY(make_tensor_map(&tA1, a.a1, a.m, a.k1, a.lda1, BM));
+    CVLM_TRY(make_tensor_map(&tB1, a.b1, brows, a.k1, a.ldb1, BN));
+    if (a.k2 > 0) {
+        CVLM_TRY(make_tensor_map(&tA2, a.a2, a.m, a.k2, a.lda2, BM));
+        CVLM_TRY(make_tensor_map(&tB2, a.b2, brows, a.k2, a.ldb2, BN));
+    } else {
+        tA2 = tA1;
+        tB2 = tB1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr_set = true;
+    }
+    const int tiles_m = (a.m + BM - 1) / BM, tiles_n = (a.n + BN - 1) / BN;
+    const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
+    GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu};
+    const int grid = tiles_m * tiles_n < num_sms() ? tiles_m * tiles_n : num_sms();
+    gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, tiles_m,
+                                                                      tiles_n, ep);
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
+}  // namespace cvlm

@@ -1,0 +1,117 @@
+"""Op-level Python wrappers over the C ABI (include/cvlm.h ``cvlm_op_*``): torch tensors in, torch
+tensors out, launches on the current CUDA stream.  Used by the parity tests and for profiling single
+kernels; the encoder itself goes through ``cvlm_encoder_forward``.  No fallbacks: CUDA tensors only."""
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cvlm ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm_bf16(a1: torch.Tensor, b1: torch.Tensor, a2: Optional[torch.Tensor] = None,
+              b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out_dtype=torch.float32,
+              gelu: bool = False, n: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m, n] = epilogue(a1 @ b1.T (+ a2 @ b2.T)).  a*: bf16 [m, k*] (last dim contiguous, any row stride),
+    b*: bf16 [rows<=n, k*].  ``n`` defaults to b1.shape[0] rounded up to a multiple of 8."""
+    _need_cuda(a1, b1, a2, b2, bias, residual, out)
+    assert a1.dtype == torch.bfloat16 and b1.dtype == torch.bfloat16 and a1.stride(1) == 1 and b1.stride(1) == 1
+    m, k1 = a1.shape
+    b_rows = b1.shape[0]
+    if n is None:
+        n = (b_rows + 7) // 8 * 8
+    if out is None:
+        out = torch.empty(m, n, device=a1.device, dtype=out_dtype)
+    k2 = 0
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and b2.dtype == torch.bfloat16 and a2.stride(1) == 1 and b2.stride(1) == 1
+        k2 = a2.shape[1]
+    lib = _lib.load()
+    _lib.check(lib.cvlm_op_gemm_bf16(
+        a1.data_ptr(), a1.stride(0), b1.data_ptr(), b1.stride(0), k1,
+        _ptr(a2), a2.stride(0) if a2 is not None else 0, _ptr(b2), b2.stride(0) if b2 is not None else 0, k2,
+        m, n, b_rows, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, res_row_mod,
+        out.data_ptr(), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0, 1 if gelu else 0,
+        _lib.stream_ptr()), "cvlm_op_gemm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, batch: int, grid: int,
+              window: int, heads: int, head_dim: int) -> torch.Tensor:
+    _need_cuda(qkv, rel_pos_h, rel_pos_w)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    out = torch.empty(qkv.shape[0], heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_attention(qkv.data_ptr(), out.data_ptr(), rel_pos_h.contiguous().data_ptr(),
+                                             rel_pos_w.contiguous().data_ptr(), batch, grid, window, heads, head_dim,
+                                             _lib.stream_ptr()), "cvlm_op_attention")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype=torch.bfloat16):
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rows, cols = x.shape
+    out = torch.empty(rows, cols, device=x.device, dtype=out_dtype)
+    _lib.check(_lib.load().cvlm_op_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                             1 if out_dtype == torch.bfloat16 else 0, rows, cols, eps,
+                                             _lib.stream_ptr()), "cvlm_op_layernorm")
+    return out
+
+
+def layernorm2d_nchw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, batch: int, tokens: int, eps: float):
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    chans = x.shape[1]
+    out = torch.empty(batch, chans, tokens, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().cvlm_op_layernorm2d_nchw(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                                    batch, tokens, chans, eps, _lib.stream_ptr()),
+               "cvlm_op_layernorm2d_nchw")
+    return out
+
+
+def im2col_patch16(img: torch.Tensor) -> torch.Tensor:
+    _need_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    b, c, h, _ = img.shape
+    g = h // 16
+    out = torch.empty(b * g * g, c * 256, device=img.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_im2col_patch16(img.data_ptr(), out.data_ptr(), b, c, h, _lib.stream_ptr()),
+               "cvlm_op_im2col_patch16")
+    return out
+
+
+def im2col_3x3(x: torch.Tensor, batch: int, grid: int) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    c = x.shape[-1]
+    out = torch.empty(batch * grid * grid, 9 * c, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_im2col_3x3(x.data_ptr(), out.data_ptr(), batch, grid, c, _lib.stream_ptr()),
+               "cvlm_op_im2col_3x3")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    out = torch.empty_like(x, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _lib.stream_ptr()),
+               "cvlm_op_cast_bf16")
+    return out
+
+
+def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> torch.Tensor:
+    _need_cuda(x0, hand, w_t, cst)
+    out = torch.empty(batch * tokens, rank_pad, device=x0.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_adapter_embed(x0.data_ptr(), hand.data_ptr(), w_t.data_ptr(), cst.data_ptr(),
+                                                 out.data_ptr(), batch, tokens, dim, rank, rank_pad,
+                                                 _lib.stream_ptr()), "cvlm_op_adapter_embed")
+    return out

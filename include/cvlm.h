@@ -1,0 +1,148 @@
+/*
+ * cvlm.h -- C ABI of the B200-native SAM-Adapter image encoder (libcvlm_b200.so).
+ *
+ * The reference (intcomp/camouflaged-vlm) has no FFI or plugin layer on this path: its boundary is
+ * the Python class models/mmseg/models/sam/image_encoder.py:25 `ImageEncoderViT`, called as
+ * `self.image_encoder(input, interm=True)` (models/sam_maskdecoder_edge.py:278, 311, 337;
+ * models/sam.py:406, 431, 456).  This header is the boundary a maintainer binds instead of that
+ * module's torch ops (ctypes stub in INTEGRATION.md; the in-tree binding is
+ * camouflaged_vlm_b200/_lib.py).  Everything is `extern "C"`, plain pointers and sizes, no torch or
+ * CUDA types: device buffers are `void*` / `float*` device addresses, the stream is the
+ * `cudaStream_t` handle passed as `void*`.
+ *
+ * Conventions
+ *   - every function returns CVLM_OK (0) or a negative error code; cvlm_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - all launches are asynchronous on `stream`; nothing synchronises the device.
+ *   - the library owns no device memory: weights, workspace and outputs are caller-allocated.
+ *   - bf16 buffers are raw uint16 bit patterns (`__nv_bfloat16`).
+ */
+#ifndef CVLM_H_
+#define CVLM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVLM_OK 0
+#define CVLM_ERR_ARG (-1)          /* null / misaligned pointer, bad shape */
+#define CVLM_ERR_CUDA (-2)         /* a CUDA runtime / driver call failed */
+#define CVLM_ERR_UNSUPPORTED (-3)  /* shape outside what the kernels implement */
+#define CVLM_ERR_MISSING (-4)      /* a required weight tensor was not registered or has the wrong size */
+#define CVLM_ERR_WORKSPACE (-5)    /* workspace too small */
+
+#define CVLM_MAX_DEPTH 64
+
+typedef void* cvlm_stream_t; /* cudaStream_t */
+
+const char* cvlm_last_error(void);
+int cvlm_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder handle.  Mirrors ImageEncoderViT.__init__ (image_encoder.py:26-44) after the Python side
+ * has resolved norm_layer / act_layer to LayerNorm(eps) / GELU.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cvlm_encoder_config {
+    int img_size;     /* image side in pixels (square), multiple of 16 */
+    int patch_size;   /* 16 */
+    int in_chans;     /* 3 */
+    int embed_dim;    /* D */
+    int depth;        /* number of blocks, <= CVLM_MAX_DEPTH */
+    int num_heads;    /* D / num_heads must be 64 or 80 */
+    int mlp_dim;      /* int(D * mlp_ratio) */
+    int out_chans;    /* neck width, multiple of 8 */
+    int window_size;  /* window side of the non-global blocks (0: every block global) */
+    int is_global[CVLM_MAX_DEPTH]; /* 1 if block i uses global attention (global_attn_indexes) */
+    int use_abs_pos;  /* pos_embed present */
+    int rank;         /* adapter width D / scale_factor (image_encoder.py:252) */
+    int rank_pad;     /* rank rounded up to a multiple of 8: one of 8,16,24,32,40 */
+    float ln_eps;     /* eps of the block LayerNorms (callers bind 1e-6) */
+    float ln2d_eps;   /* eps of LayerNorm2d (common.py:32, 1e-6) */
+} cvlm_encoder_config;
+
+typedef struct cvlm_encoder cvlm_encoder;
+
+int cvlm_encoder_create(const cvlm_encoder_config* cfg, cvlm_encoder** out);
+int cvlm_encoder_destroy(cvlm_encoder* enc);
+
+/* Register one packed weight tensor (device pointer, 16-byte aligned).  Names and layouts are listed
+ * in DESIGN.md section "Packed weights"; camouflaged_vlm_b200/packing.py derives them from the reference
+ * state_dict.  Re-registering a name replaces it (load_state_dict). */
+int cvlm_encoder_set_tensor(cvlm_encoder* enc, const char* name, const void* dev_ptr, long long nbytes);
+
+/* Scratch bytes needed by cvlm_encoder_forward for `batch` images. */
+long long cvlm_encoder_workspace_bytes(const cvlm_encoder* enc, int batch);
+
+/* ImageEncoderViT.forward(x, interm) (image_encoder.py:132-155).
+ *   images     fp32 NCHW [batch, in_chans, img, img], device
+ *   highpass   fp32 NCHW, same shape: PromptGenerator.fft(images, 0.25) (:332-353), device
+ *   out        fp32 NCHW [batch, out_chans, g, g], device
+ *   interm     NULL, or one device pointer per global block (in block order), each fp32 NHWC
+ *              [batch, g, g, D]: receives the residual stream after that block; the Python module
+ *              hands callers .permute(0,3,1,2) views of these, exactly like the reference (:148)
+ *   workspace  device scratch of at least cvlm_encoder_workspace_bytes(enc, batch), 256-byte aligned */
+int cvlm_encoder_forward(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
+                         float* const* interm, void* workspace, long long workspace_bytes, cvlm_stream_t stream);
+
+/* Same, but stops after block `stop_after_block` (0-based; -1 = after the stem, before block 0's
+ * prompt add is NOT included: the stem output already holds x + pos_embed + prompt_0) and copies the
+ * fp32 NHWC residual stream [batch*g*g, D] to `x_out`.  Parity-debug aid, not used by the product path. */
+int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const float* highpass, int batch,
+                                 int stop_after_block, float* x_out, void* workspace, long long workspace_bytes,
+                                 cvlm_stream_t stream);
+
+/* Number of kernel launches the last cvlm_encoder_forward on this handle issued (for bench.py's
+ * gpu_launches claim). */
+long long cvlm_encoder_last_launch_count(const cvlm_encoder* enc);
+
+/* Per-kernel timing.  With profiling enabled every launch of cvlm_encoder_forward is bracketed by CUDA
+ * events on `stream`; cvlm_encoder_get_profile waits for them, sums the elapsed milliseconds and the
+ * launch counts per kind since the previous call, and resets.  Kinds, in order: qkv GEMM, proj GEMM,
+ * lin1 GEMM, lin2 GEMM, other GEMMs (stem, adapter, neck), window attention, global attention,
+ * LayerNorm, other row kernels. */
+#define CVLM_PROF_KINDS 9
+int cvlm_encoder_set_profiling(cvlm_encoder* enc, int enable);
+int cvlm_encoder_get_profile(cvlm_encoder* enc, float* ms_by_kind, int* launches_by_kind);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op-level entry points (the kernels behind the encoder; used by the parity tests and profiling).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out = epilogue(A1 * B1^T [+ A2 * B2^T]); A* bf16 [m, k*] row stride lda*, B* bf16 [b_rows, k*] row
+ * stride ldb* (weights, nn.Linear layout), rows >= b_rows read as zero.  Epilogue: + bias[n] (fp32),
+ * optional exact-erf GELU, + residual fp32 [*, ldr] (row = row % res_row_mod when res_row_mod > 0),
+ * store fp32 or bf16 with row stride ldo.  n % 8 == 0.  tcgen05 / TMEM / TMA kernel. */
+int cvlm_op_gemm_bf16(const void* a1, long long lda1, const void* b1, long long ldb1, int k1, const void* a2,
+                      long long lda2, const void* b2, long long ldb2, int k2, int m, int n, int b_rows,
+                      const float* bias, const float* residual, long long ldr, int res_row_mod, void* out,
+                      long long ldo, int out_bf16, int act_gelu, cvlm_stream_t stream);
+
+/* Window (window>0) or global (window==0) attention with decomposed rel-pos on the token-major qkv
+ * buffer bf16 [batch*g*g, 3*heads*head_dim] (K and V stored without bias); out bf16 [batch*g*g, D]. */
+int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
+                      int grid_side, int window, int heads, int head_dim, cvlm_stream_t stream);
+
+/* nn.LayerNorm over the last dim of fp32 [rows, cols]; out bf16 (out_bf16=1) or fp32. */
+int cvlm_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_bf16,
+                      long long rows, int cols, float eps, cvlm_stream_t stream);
+
+/* LayerNorm2d of token-major fp32 [batch*tokens, chans], written as NCHW fp32 [batch, chans, tokens]. */
+int cvlm_op_layernorm2d_nchw(const float* x, const float* gamma, const float* beta, float* out_nchw, int batch,
+                             int tokens, int chans, float eps, cvlm_stream_t stream);
+
+/* fp32 NCHW image -> bf16 patch matrix [batch*g*g, chans*256] for a 16x16 stride-16 conv. */
+int cvlm_op_im2col_patch16(const float* img, void* out, int batch, int chans, int img_size, cvlm_stream_t stream);
+
+/* bf16 NHWC [batch, g, g, chans] -> bf16 [batch*g*g, 9*chans] for a 3x3 pad-1 conv. */
+int cvlm_op_im2col_3x3(const void* x_nhwc, void* out, int batch, int grid_side, int chans, cvlm_stream_t stream);
+
+int cvlm_op_cast_bf16(const float* x, void* out, long long n, cvlm_stream_t stream);
+
+/* t = bf16(hand + cst + W_eg * scramble(x0)); see rowops.cu / DESIGN.md "adapter". */
+int cvlm_op_adapter_embed(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,
+                          int batch, int tokens, int dim, int rank, int rank_pad, cvlm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVLM_H_ */

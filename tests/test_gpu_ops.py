@@ -1,0 +1,157 @@
+"""Kernel-level parity on the B200: every cvlm_op_* (through the C ABI) against a torch fp32
+restatement of the same op on the same (bf16-rounded) inputs.  Tolerances are stated per test:
+bf16 outputs carry one rounding (2^-9 relative), fp32 outputs only accumulation-order noise."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from camouflaged_vlm_b200 import check_path as cp   # noqa: E402
+from camouflaged_vlm_b200 import ops                # noqa: E402
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _randn(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+@pytest.mark.parametrize("rows,cols", [(4096, 1280), (1000, 768), (77, 256), (8, 64), (333, 1024)])
+def test_layernorm(rows, cols):
+    x = _randn(rows, cols, seed=1) * 3 + 0.5
+    w, b = 1 + 0.1 * _randn(cols, seed=2), 0.1 * _randn(cols, seed=3)
+    want = torch.nn.functional.layer_norm(x, (cols,), w, b, 1e-6)
+    assert _rel(ops.layernorm(x, w, b, 1e-6, torch.float32), want) < 2e-6
+    assert _rel(ops.layernorm(x, w, b, 1e-6, torch.bfloat16).float(), want) < 4e-3
+    assert torch.equal(ops.layernorm(x, w, b, 1e-6, torch.bfloat16), ops.layernorm(x, w, b, 1e-6, torch.float32).bfloat16())
+
+
+def test_layernorm2d_nchw():
+    for batch, tokens, chans in [(2, 4096, 256), (1, 324, 256), (3, 100, 16)]:
+        x = _randn(batch * tokens, chans, seed=4) * 2 - 1
+        w, b = 1 + 0.1 * _randn(chans, seed=5), 0.1 * _randn(chans, seed=6)
+        want = cp.layernorm2d_nchw(x, w, b, batch, tokens, 1e-6)
+        assert _rel(ops.layernorm2d_nchw(x, w, b, batch, tokens, 1e-6), want) < 2e-6
+
+
+def test_im2col_and_cast_are_bit_exact():
+    img = _randn(2, 3, 160, 160, seed=7)
+    assert torch.equal(ops.im2col_patch16(img), cp.im2col_patch16(img).bfloat16())
+    x = _randn(2 * 10 * 10, 16, seed=8, dtype=torch.bfloat16)
+    assert torch.equal(ops.im2col_3x3(x, 2, 10), cp.im2col_3x3(x, 2, 10))
+    x = _randn(2 * 64 * 64, 256, seed=8, dtype=torch.bfloat16)
+    assert torch.equal(ops.im2col_3x3(x, 2, 64), cp.im2col_3x3(x, 2, 64))
+    y = _randn(1000, 64, seed=9)
+    assert torch.equal(ops.cast_bf16(y), y.bfloat16())
+
+
+@pytest.mark.parametrize("batch,tokens,dim,rank,rp", [(2, 100, 64, 2, 8), (1, 324, 320, 10, 16), (2, 4096, 1280, 40, 40)])
+def test_adapter_embed(batch, tokens, dim, rank, rp):
+    x0 = _randn(batch * tokens, dim, seed=10)
+    hand = _randn(batch * tokens, rp, seed=11)
+    w_t = _randn(dim, rp, seed=12, scale=0.02)
+    w_t[:, rank:] = 0
+    cst = _randn(tokens, rp, seed=13, scale=0.1)
+    want = cp.adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rp)
+    got = ops.adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rp).float()
+    assert _rel(got, want) < 4e-3                   # one bf16 rounding of the output
+    assert torch.all(got[:, rank:] == 0)
+
+
+GEMM_SHAPES = [
+    # m, n, k   (tile is 128 x 256 x 64)
+    (128, 256, 64), (128, 256, 128), (256, 512, 256), (384, 1280, 1280), (1000, 264, 200),
+    (4096, 3840, 1280), (4096, 1280, 5120), (300, 40, 768), (4096, 1280, 40),
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_plain(m, n, k):
+    a = _randn(m, k, seed=20, dtype=torch.bfloat16)
+    b = _randn(n, k, seed=21, dtype=torch.bfloat16, scale=0.05)
+    want = a.float() @ b.float().t()
+    got = ops.gemm_bf16(a, b, n=n)
+    assert got.shape == (m, n)
+    assert _rel(got, want) < 1e-5                    # exact bf16 products, fp32 accumulation
+    got16 = ops.gemm_bf16(a, b, n=n, out_dtype=torch.bfloat16)
+    assert _rel(got16.float(), want) < 4e-3
+
+
+def test_gemm_epilogues():
+    m, n, k = 512, 512, 320
+    a = _randn(m, k, seed=22, dtype=torch.bfloat16)
+    b = _randn(n, k, seed=23, dtype=torch.bfloat16, scale=0.05)
+    bias = _randn(n, seed=24)
+    res = _randn(m, n, seed=25)
+    base = a.float() @ b.float().t()
+    assert _rel(ops.gemm_bf16(a, b, bias=bias), base + bias) < 1e-5
+    assert _rel(ops.gemm_bf16(a, b, bias=bias, gelu=True), torch.nn.functional.gelu(base + bias)) < 1e-5
+    assert _rel(ops.gemm_bf16(a, b, bias=bias, residual=res), base + bias + res) < 1e-5
+    # in-place residual (out aliases residual), as the proj / lin2 epilogues run it
+    buf = res.clone()
+    ops.gemm_bf16(a, b, bias=bias, residual=buf, out=buf)
+    assert _rel(buf, base + bias + res) < 1e-5
+    # row-periodic residual (pos_embed broadcast over the batch)
+    pos = _randn(128, n, seed=26)
+    want = base + bias + pos.repeat(m // 128, 1)
+    assert _rel(ops.gemm_bf16(a, b, bias=bias, residual=pos, res_row_mod=128), want) < 1e-5
+
+
+def test_gemm_two_k_segments_and_strided_operands():
+    m, n, k1, rp, depth = 640, 1280, 512, 40, 4
+    a1 = _randn(m, k1, seed=27, dtype=torch.bfloat16)
+    b1 = _randn(n, k1, seed=28, dtype=torch.bfloat16, scale=0.05)
+    gall = _randn(m, depth * rp, seed=29, dtype=torch.bfloat16)
+    b2 = _randn(n, rp, seed=30, dtype=torch.bfloat16, scale=0.05)
+    res = _randn(m, n, seed=31)
+    for i in range(depth):
+        a2 = gall[:, i * rp:(i + 1) * rp]            # column slice: row stride depth*rp, 16-byte aligned base
+        want = a1.float() @ b1.float().t() + a2.float() @ b2.float().t() + res
+        assert _rel(ops.gemm_bf16(a1, b1, a2, b2, residual=res), want) < 1e-5
+    # weights with fewer rows than n (zero rows beyond): adapter PatchEmbed2 output padded 10 -> 16
+    bw = _randn(10, k1, seed=32, dtype=torch.bfloat16, scale=0.05)
+    got = ops.gemm_bf16(a1, bw, n=16)
+    assert _rel(got[:, :10], a1.float() @ bw.float().t()) < 1e-5
+    assert torch.all(got[:, 10:] == 0)
+
+
+def test_gemm_rejects_bad_arguments():
+    from camouflaged_vlm_b200._lib import CvlmError
+    a = _randn(128, 64, dtype=torch.bfloat16)
+    b = _randn(12, 64, dtype=torch.bfloat16)
+    with pytest.raises(CvlmError):
+        ops.gemm_bf16(a, b, n=12)                    # n % 8 != 0
+    with pytest.raises(RuntimeError):
+        ops.gemm_bf16(a.cpu(), b.cpu())              # no CPU fallback
+
+
+ATT_CASES = [
+    # batch, grid, window, heads, head_dim
+    (2, 10, 4, 2, 64),      # padded windows, generic path
+    (1, 18, 14, 4, 80),     # ViT-H window size, 2x2 windows with padding
+    (1, 18, 0, 4, 80),      # global, generic path (grid != 64)
+    (1, 10, 14, 2, 80),     # window larger than the grid: one padded window
+    (2, 64, 14, 2, 80),     # ViT-H windowed geometry (5x5 windows over 64x64)
+    (1, 64, 0, 2, 80),      # ViT-H global geometry: row-aligned fast path
+    (1, 64, 0, 2, 64),      # ViT-B/L global
+    (1, 16, 14, 4, 64),
+]
+
+
+@pytest.mark.parametrize("batch,grid,window,heads,hd", ATT_CASES)
+def test_attention(batch, grid, window, heads, hd):
+    d = heads * hd
+    s = window if window > 0 else grid
+    qkv = _randn(batch * grid * grid, 3 * d, seed=40, dtype=torch.bfloat16, scale=0.8)
+    relh = _randn(2 * s - 1, hd, seed=41, dtype=torch.bfloat16, scale=0.1)
+    relw = _randn(2 * s - 1, hd, seed=42, dtype=torch.bfloat16, scale=0.1)
+    want = cp.attention(qkv, relh, relw, batch, grid, window, heads, hd)
+    got = ops.attention(qkv, relh, relw, batch, grid, window, heads, hd).float()
+    # bf16 P and bf16 output: ~2^-8 relative
+    assert _rel(got, want) < 8e-3
