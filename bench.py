@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: SAM ViT-H ImageEncoderViT forward, img/s at 1024^2 (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+
+A "step" is one forward of the encoder over a batch of 32 synthetic images per GPU (BASELINE.json
+configs[1]), called the way the cascade calls it (``image_encoder(x, interm=True)``,
+models/sam_maskdecoder_edge.py:337).  One JSON line is printed by rank 0:
+
+  value      whole-job img/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public nn.Module call with HOST buffers: pinned H2D of the batch,
+             forward, (N>1: NCCL all-gather of the embeddings), D2H of the embeddings, every step
+  roofline   the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of its launches / their CUDA-event
+             time, against the measured dense-bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference) timed on this box's host cores, 1 image
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vit_h_image_encoder_throughput_1024px"
+UNIT = "img/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--model", default="vit_h")
+    ap.add_argument("--no-interm", action="store_true", help="call forward(x) instead of forward(x, interm=True)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, cfg, world):
+    return {
+        "workload": f"SAM {args.model} ImageEncoderViT forward (interm={not args.no_interm}), bf16, batch "
+                    f"{args.batch} per GPU, {cfg.img_size}x{cfg.img_size} synthetic images, random-init weights "
+                    "(BASELINE.json configs[1]; configs[2] sharding at N>1)",
+        "batch_per_gpu": args.batch,
+        "global_batch": args.batch * world,
+        "img_size": cfg.img_size,
+        "parallelism": f"dp{world} (batch-sharded, weights replicated)",
+        "l2": "inputs larger than L2: 12.6 MB/image input, ~85 MB/image of activations streamed per block",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def gemm_flops_per_image(cfg):
+    """Algorithmic FLOPs of the launches of the tcgen05 GEMM kernel (everything in cfg.flops_per_image()
+    except attention and the adapter's SIMT embedding kernel)."""
+    n, d, r = cfg.tokens, cfg.embed_dim, cfg.rank
+    kp = cfg.in_chans * cfg.patch_size ** 2
+    lin = cfg.depth * (2 * n * d * 3 * d + 2 * n * d * d + 2 * 2 * n * d * cfg.mlp_dim)
+    stem = 2 * n * kp * d + 2 * n * kp * r
+    adapter = cfg.depth * (2 * n * r * r + 2 * n * r * d)
+    neck = 2 * n * d * cfg.out_chans + 2 * n * cfg.out_chans * cfg.out_chans * 9
+    return float(lin + stem + adapter + neck)
+
+
+# ----------------------------------------------------------------------------------------------
+def time_oracle_cpu(cfg, sd_cpu, steps, warmup, budget_s=240.0):
+    """One image per step on all host threads.  Returns (img/s, seconds per step, steps run, warmups run)."""
+    import torch
+    from camouflaged_vlm_b200.synth import seeded_images
+    from oracle import encoder_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = seeded_images(cfg, 1, 0)
+    t0 = time.perf_counter()
+    orc.encoder_forward(sd_cpu, cfg, x, interm=True)          # first pass doubles as warm-up / calibration
+    first = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and (warm_done + 1 + max(1, steps)) * first < budget_s:
+        orc.encoder_forward(sd_cpu, cfg, x, interm=True)
+        warm_done += 1
+    steps_run = max(1, min(steps, int((budget_s - warm_done * first) / max(first, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(steps_run):
+        orc.encoder_forward(sd_cpu, cfg, x, interm=True)
+    dt = (time.perf_counter() - t0) / steps_run
+    return 1.0 / dt, dt, steps_run, warm_done
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores.
+    The reference is Python/torch and cannot travel to the GPU box (no /root/reference there), so this
+    arm times the oracle port (oracle/encoder_oracle.py, pinned to the reference's outputs)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    from camouflaged_vlm_b200 import PRESETS
+    from camouflaged_vlm_b200.synth import seeded_state_dict
+    cfg = PRESETS[args.model]
+    sd = seeded_state_dict(cfg, 0)
+    with torch.no_grad():
+        ips, dt, steps_run, warm_run = time_oracle_cpu(cfg, sd, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": steps_run,
+        "warmup": warm_run, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, world),
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 image per step (a batch-32 step is 32 independent images; the CPU rate is per image), "
+                                   f"{steps_run} timed steps after {warm_run} warm-up (requested {args.steps}/{args.warmup}, "
+                                   "capped to a 4-minute budget)"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from camouflaged_vlm_b200 import PRESETS, _lib, build_encoder
+    from camouflaged_vlm_b200.synth import param_shapes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = PRESETS[args.model]
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    interm = not args.no_interm
+
+    # random-init weights of the architecture (same recipe as synth.seeded_state_dict, generated on the GPU)
+    model = build_encoder(cfg).eval().to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            p.copy_(torch.randn(p.shape, generator=gen, device=dev) * 0.02)
+            if name.endswith(("norm1.weight", "norm2.weight", "neck.1.weight", "neck.3.weight")):
+                p.add_(1.0)
+    assert set(dict(model.named_parameters())) == set(param_shapes(cfg))
+    x_dev = torch.randn(B, cfg.in_chans, cfg.img_size, cfg.img_size, generator=gen, device=dev)
+
+    def step(x):
+        with torch.no_grad():
+            return model(x, interm=interm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(W):
+        step(x_dev)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step(x_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.last_launch_count * K
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- per-kernel CUDA-event timing over the same K steps (events bracket every launch on the stream)
+    lib = _lib.load()
+    lib.cvlm_encoder_set_profiling(model._handle, 1)
+    for _ in range(K):
+        step(x_dev)
+    torch.cuda.synchronize()
+    import ctypes as C
+    ms_kind = (C.c_float * len(_lib.PROF_KINDS))()
+    n_kind = (C.c_int * len(_lib.PROF_KINDS))()
+    _lib.check(lib.cvlm_encoder_get_profile(model._handle, ms_kind, n_kind), "get_profile")
+    lib.cvlm_encoder_set_profiling(model._handle, 0)
+    kernels = {k: {"ms_per_step": ms_kind[i] / K, "launches_per_step": n_kind[i] // K} for i, k in enumerate(_lib.PROF_KINDS)}
+    gemm_ms = sum(kernels[k]["ms_per_step"] for k in _lib.PROF_KINDS if k.startswith("gemm"))
+    gemm_launches = sum(kernels[k]["launches_per_step"] for k in _lib.PROF_KINDS if k.startswith("gemm"))
+    peaks = load_peaks()
+    gemm_tflops = B * gemm_flops_per_image(cfg) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    step_tflops = B * cfg.flops_per_image() / (ms_total / K * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm_tflops, "peak": peaks["sustained"],
+        "unit": "TFLOP/s", "frac": gemm_tflops / peaks["sustained"], "traffic": None,
+        "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+        "launches_per_step": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+        "share_of_step": gemm_ms / (ms_total / K),
+        "whole_step": {"achieved_tflops": step_tflops, "frac_of_sustained": step_tflops / peaks["sustained"],
+                       "frac_of_burst": step_tflops / peaks["burst"], "frac_of_nominal_2250": step_tflops / 2250.0,
+                       "flops_per_image": cfg.flops_per_image()},
+    }
+
+    # ---- end to end through the public call with host buffers
+    e2e = None
+    if not args.skip_e2e:
+        x_host = torch.empty(B, cfg.in_chans, cfg.img_size, cfg.img_size, pin_memory=True)
+        x_host.copy_(x_dev)
+        out_host = torch.empty(B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
+        x_in = torch.empty_like(x_dev)
+        gathered = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev) if world > 1 else None
+
+        def e2e_step():
+            x_in.copy_(x_host, non_blocking=True)
+            out = step(x_in)
+            emb = out[0] if interm else out
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, emb)      # embeddings gathered over NVLink (configs[2])
+            out_host.copy_(emb, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * out_host.numel() * 4,
+               "ms_per_step": ms_e2e / K,
+               "note": "pinned host -> device copy, forward(x, interm), "
+                       + ("NCCL all_gather_into_tensor of the embeddings, " if world > 1 else "")
+                       + "device -> pinned host copy of the [B,256,64,64] embedding; whole-job bytes"}
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            ips, dt, steps_run, _ = time_oracle_cpu(cfg, sd_cpu, 1, 1, budget_s=90.0)
+        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"oracle (CPU restatement of the reference, fp32, torch {torch.__version__}) on 1 image of the "
+                         f"same workload, {steps_run} timed pass after 1 warm-up, {dt:.1f} s per image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

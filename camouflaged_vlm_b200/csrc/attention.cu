@@ -401,8 +401,8 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
                      int window, int heads, int head_dim, cudaStream_t stream) {
     if (!qkv || !out || !relh || !relw) return set_error(CVLM_ERR_ARG, "attention: null pointer");
     if (batch <= 0 || grid_side <= 0 || heads <= 0) return set_error(CVLM_ERR_ARG, "attention: bad sizes");
-    if (head_dim != 64 && head_dim != 80)
-        return set_error(CVLM_ERR_UNSUPPORTED, "attention: head_dim must be 64 or 80 (ViT-B/L/H)");
+    if (head_dim != 32 && head_dim != 64 && head_dim != 80)
+        return set_error(CVLM_ERR_UNSUPPORTED, "attention: head_dim must be 32, 64 or 80");
     AttnParams p;
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.out = static_cast<__nv_bfloat16*>(out);
@@ -421,7 +421,9 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     const bool aligned = (p.S == ATT_BK);
     if (head_dim == 80)
         return aligned ? launch_attention<80, true>(p, batch, stream) : launch_attention<80, false>(p, batch, stream);
-    return aligned ? launch_attention<64, true>(p, batch, stream) : launch_attention<64, false>(p, batch, stream);
+    if (head_dim == 64)
+        return aligned ? launch_attention<64, true>(p, batch, stream) : launch_attention<64, false>(p, batch, stream);
+    return aligned ? launch_attention<32, true>(p, batch, stream) : launch_attention<32, false>(p, batch, stream);
 }
 
 }  // namespace cvlm

@@ -363,7 +363,8 @@ int cvlm_encoder_create(const cvlm_encoder_config* cfg, cvlm_encoder** out) {
     if (c.depth <= 0 || c.depth > CVLM_MAX_DEPTH) return set_error(CVLM_ERR_UNSUPPORTED, "create: depth out of range");
     if (c.num_heads <= 0 || c.embed_dim % c.num_heads) return set_error(CVLM_ERR_ARG, "create: embed_dim %% num_heads != 0");
     const int hd = c.embed_dim / c.num_heads;
-    if (hd != 64 && hd != 80) return set_error(CVLM_ERR_UNSUPPORTED, "create: head_dim %d (supported: 64, 80)", hd);
+    if (hd != 32 && hd != 64 && hd != 80)
+        return set_error(CVLM_ERR_UNSUPPORTED, "create: head_dim %d (supported: 32, 64, 80)", hd);
     if (c.embed_dim % 8 || c.mlp_dim % 8 || c.out_chans % 8)
         return set_error(CVLM_ERR_UNSUPPORTED, "create: embed_dim, mlp_dim, out_chans must be multiples of 8");
     if (c.rank <= 0 || c.rank_pad < c.rank || c.rank_pad % 8 || c.rank_pad > 40)

@@ -48,7 +48,7 @@ typedef struct cvlm_encoder_config {
     int in_chans;     /* 3 */
     int embed_dim;    /* D */
     int depth;        /* number of blocks, <= CVLM_MAX_DEPTH */
-    int num_heads;    /* D / num_heads must be 64 or 80 */
+    int num_heads;    /* D / num_heads must be 32, 64 or 80 */
     int mlp_dim;      /* int(D * mlp_ratio) */
     int out_chans;    /* neck width, multiple of 8 */
     int window_size;  /* window side of the non-global blocks (0: every block global) */

@@ -132,6 +132,7 @@ def test_gemm_rejects_bad_arguments():
 
 
 ATT_CASES = [
+    (2, 10, 4, 2, 32),      # head_dim 32 (tiny test config)
     # batch, grid, window, heads, head_dim
     (2, 10, 4, 2, 64),      # padded windows, generic path
     (1, 18, 14, 4, 80),     # ViT-H window size, 2x2 windows with padding

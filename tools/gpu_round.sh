@@ -1,0 +1,33 @@
+#!/bin/bash
+# One GPU-box visit: encoder parity tests, parity report, bench line, ncu launch list, ncu full capture of
+# the GEMM kernel.  Everything lands in gpurun_out/ with the tag given as $1.
+TAG=${1:-r1}
+O=gpurun_out
+mkdir -p $O
+fault() { grep -qiE "illegal memory|launch failure|unspecified launch|misaligned address|mbarrier timeout|CUDA error" "$1"; }
+echo "=== tests" | tee $O/round_$TAG.log
+timeout 900 python -m pytest -q -m gpu tests/ 2>&1 | tail -15 | tee -a $O/round_$TAG.log
+if fault $O/round_$TAG.log; then echo "fault in tests, stopping"; exit 3; fi
+echo "=== parity" | tee -a $O/round_$TAG.log
+timeout 600 python tools/parity_report.py $O/parity_$TAG.json 2>&1 | tail -8 | tee -a $O/round_$TAG.log
+echo "=== smoke" | tee -a $O/round_$TAG.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee -a $O/round_$TAG.log
+echo "=== bench" | tee -a $O/round_$TAG.log
+timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err
+echo "bench exit $?" | tee -a $O/round_$TAG.log
+tail -c 3000 $O/bench_$TAG.json | tee -a $O/round_$TAG.log
+tail -5 $O/bench_$TAG.err | tee -a $O/round_$TAG.log
+if [ "$2" == "noncu" ]; then exit 0; fi
+KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|layernorm_kernel|im2col|cast_bf16_kernel|adapter_embed_kernel|layernorm_nchw_kernel'
+BENCH="python bench.py --steps 1 --warmup 3 --batch 8 --skip-cpu-baseline --skip-e2e"
+echo "=== ncu launch list" | tee -a $O/round_$TAG.log
+$BENCH > $O/plain_$TAG.log 2>&1 && \
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 260 -c 260 --csv \
+    --log-file $O/launches_$TAG.csv $BENCH > $O/ncu_list_$TAG.log 2>&1
+echo "ncu list exit $?" | tee -a $O/round_$TAG.log
+echo "=== ncu full (gemm)" | tee -a $O/round_$TAG.log
+$BENCH > $O/plain2_$TAG.log 2>&1 && \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05_kernel -s 30 -c 4 \
+    -o $O/prof_gemm_$TAG -f $BENCH > $O/ncu_full_$TAG.log 2>&1
+echo "ncu full exit $?" | tee -a $O/round_$TAG.log
+tail -3 $O/ncu_full_$TAG.log | tee -a $O/round_$TAG.log
