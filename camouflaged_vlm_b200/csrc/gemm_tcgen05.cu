@@ -28,7 +28,9 @@ constexpr int B_STAGE = BN * BK * 2;     // 32 KB
 constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGING = EPI_WARPS * 4096;   // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(GEMM_SMEM <= 232448, "exceeds the 227 KB shared memory of one CTA");
 
 struct GemmEpi {
     const float* bias;
@@ -41,7 +43,20 @@ struct GemmEpi {
     int act_gelu;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, common.py:26).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
+// far below the bf16 rounding of the output) on two MUFU ops + 8 FMA instead of libdevice erff's
+// branchy ~30 instructions: the lin1 epilogue was the bottleneck of that GEMM (profiles/r1a).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = __expf(-z * z);
+    const float erf_abs = fmaf(-p * t, e, 1.0f);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -52,7 +67,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base;
     const uint32_t sB = base + STAGES * A_STAGE;
-    const uint32_t bars = sB + STAGES * B_STAGE;
+    const uint32_t staging = sB + STAGES * B_STAGE;
+    const uint32_t bars = staging + EPI_STAGING;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
@@ -146,9 +162,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps =====================
+        // TMEM hands each thread one accumulator ROW (lane = row).  Storing that way touches 32 different
+        // 128-byte lines per warp instruction and the LSU serialises them (profiles/r1a: tensor pipe 28-58 %
+        // active on the K=1280 GEMMs).  Each warp therefore transposes its 32x32 fp32 chunk through a
+        // private, XOR-swizzled 4 KB shared-memory tile so that global loads/stores run along rows:
+        // 8 lanes x 16 B = one full 128-byte line of the fp32 output / residual per row.
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
         const int half = ew >> 2;           // which 128 of the 256 accumulator columns
+        const uint32_t stg = staging + ew * 4096;
         const float* __restrict__ bias = ep.bias;
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
@@ -156,13 +178,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
             tc_fence_after();
-            const int row = m0 + quad * 32 + lane;
-            const bool row_ok = row < M;
-            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
-            const float* res_row = ep.residual ? ep.residual + rrow * ep.ldr : nullptr;
+            const int row_base = m0 + quad * 32;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int col0 = n0 + half * 128 + c * 32;
+                // fp32 path: issue the chunk's 8 residual loads first, as one batch.  out may alias residual
+                // (in-place shortcut add), so loads interleaved with the stores below would be serialised
+                // behind them by the compiler and expose a full memory latency per row group.
+                float4 rr[8];
+                const bool use_res = ep.residual != nullptr && !ep.out_bf16;
+                if (use_res) {
+                    const int col = col0 + (lane & 7) * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row_base + 4 * i + (lane >> 3);
+                        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < M && col < N) {
+                            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                            rr[i] = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
+                        }
+                    }
+                }
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128 + c * 32, v);
                 tmem_ld_wait(v);
@@ -172,47 +208,70 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
-                if (!row_ok || col0 >= N) continue;
+                if (col0 >= N || row_base >= M) continue;   // warp-uniform
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = col0 + j;
-                    if (col >= N) break;     // N is a multiple of 8, so groups of 4 are all-or-nothing
-                    float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                           __uint_as_float(v[j + 3]));
-                    if (bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
-                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                    }
-                    if (ep.act_gelu) {
-                        x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
-                    }
-                    if (res_row) {
-                        const float4 rr = *reinterpret_cast<const float4*>(res_row + col);
-                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-                    }
-                    v[j] = __float_as_uint(x.x); v[j + 1] = __float_as_uint(x.y);
-                    v[j + 2] = __float_as_uint(x.z); v[j + 3] = __float_as_uint(x.w);
-                }
-                if (ep.out_bf16) {
-                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+                for (int q = 0; q < 8; ++q)
+                    st_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                if (!ep.out_bf16) {
+                    const int cq = lane & 7, rsub = lane >> 3;
+                    const int col = col0 + cq * 4;
+                    const bool col_ok = col < N;           // N % 8 == 0: groups of 4 are all-or-nothing
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias && col_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (col0 + j >= N) break;
-                        uint4 pk;
-                        pk.x = pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                        pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                        pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                        *reinterpret_cast<uint4*>(o + j) = pk;
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + rsub;
+                        const int row = row_base + r;
+                        float4 x = ld_shared_f4(stg + r * 128 + ((cq ^ (r & 7)) << 4));
+                        if (row < M && col_ok) {
+                            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                            if (ep.act_gelu) {
+                                x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                            }
+                            if (use_res) {
+                                x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
+                            }
+                            *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = x;
+                        }
                     }
                 } else {
-                    float* o = static_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ldo + col0;
+                    const int c8 = lane & 3, rsub = lane >> 2;
+                    const int col = col0 + c8 * 8;
+                    const bool col_ok = col < N;           // N % 8 == 0
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (bias && col_ok) {
+                        b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                        b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col0 + j >= N) break;
-                        *reinterpret_cast<uint4*>(o + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 8 * i + rsub;
+                        const int row = row_base + r;
+                        float4 x0 = ld_shared_f4(stg + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
+                        float4 x1 = ld_shared_f4(stg + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+                        if (row < M && col_ok) {
+                            x0.x += b0.x; x0.y += b0.y; x0.z += b0.z; x0.w += b0.w;
+                            x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+                            if (ep.act_gelu) {
+                                x0.x = gelu_erf(x0.x); x0.y = gelu_erf(x0.y); x0.z = gelu_erf(x0.z); x0.w = gelu_erf(x0.w);
+                                x1.x = gelu_erf(x1.x); x1.y = gelu_erf(x1.y); x1.z = gelu_erf(x1.z); x1.w = gelu_erf(x1.w);
+                            }
+                            if (ep.residual) {
+                                const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                                const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
+                                const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col + 4);
+                                x0.x += r0.x; x0.y += r0.y; x0.z += r0.z; x0.w += r0.w;
+                                x1.x += r1.x; x1.y += r1.y; x1.z += r1.z; x1.w += r1.w;
+                            }
+                            uint4 pk;
+                            pk.x = pack_bf16(x0.x, x0.y); pk.y = pack_bf16(x0.z, x0.w);
+                            pk.z = pack_bf16(x1.x, x1.y); pk.w = pack_bf16(x1.z, x1.w);
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = pk;
+                        }
                     }
                 }
+                __syncwarp();   // staging tile is rewritten by the next chunk
             }
         }
     }

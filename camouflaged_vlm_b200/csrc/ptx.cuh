@@ -138,6 +138,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---------------------------------------------------------------- legacy tensor path (attention v1)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
