@@ -17,6 +17,8 @@
 //
 // v1 math path: mma.sync m16n8k16 bf16 with fp32 accumulation, flash-style online softmax in the
 // exp2 domain, K/V tiles double-buffered with cp.async.  (tcgen05 port: see DESIGN.md roadmap.)
+#include <stdlib.h>
+
 #include "cvlm_internal.cuh"
 #include "ptx.cuh"
 
@@ -418,6 +420,11 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     if (p.S > 64) return set_error(CVLM_ERR_UNSUPPORTED, "attention: window / grid side > 64 tokens");
     if (static_cast<long long>(batch) * p.nW * p.nW > 65535)
         return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch * windows exceeds grid.z; split the batch");
+    // 64x64 global blocks run on the tcgen05 kernel (attention_tc.cu); CVLM_ATTN_LEGACY=1 forces the
+    // mma.sync kernel below (A/B comparisons, bisecting).
+    static const bool legacy = getenv("CVLM_ATTN_LEGACY") != nullptr && getenv("CVLM_ATTN_LEGACY")[0] == '1';
+    if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80))
+        return attention_global_tc_launch(qkv, out, relh, relw, batch, heads, head_dim, stream);
     const bool aligned = (p.S == ATT_BK);
     if (head_dim == 80)
         return aligned ? launch_attention<80, true>(p, batch, stream) : launch_attention<80, false>(p, batch, stream);

@@ -51,6 +51,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                      int window, int heads, int head_dim, cudaStream_t stream);
 
+int attention_global_tc_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
+                               int head_dim, cudaStream_t stream);
+
 // ---- row kernels (rowops.cu)
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
                      int cols, float eps, cudaStream_t stream);
