@@ -30,9 +30,9 @@ inline EncodeTiledFn get_encode_fn() {
 struct MapSpec {
     const void* ptr;
     int rank;
-    unsigned long long dims[4];      // elements, innermost first
-    unsigned long long strides[3];   // bytes, for dims 1..rank-1
-    unsigned box[4];
+    unsigned long long dims[5];      // elements, innermost first
+    unsigned long long strides[4];   // bytes, for dims 1..rank-1
+    unsigned box[5];
     bool operator==(const MapSpec& o) const { return memcmp(this, &o, sizeof(MapSpec)) == 0; }
 };
 struct MapSpecHash {
@@ -59,8 +59,9 @@ inline int make_tensor_map_bf16(CUtensorMap* out, MapSpec spec) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(CVLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (reinterpret_cast<uintptr_t>(spec.ptr) & 15) return set_error(CVLM_ERR_ARG, "tensor map: base not 16-byte aligned");
-    cuuint64_t dims[4], strides[3];
-    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    if (spec.rank < 1 || spec.rank > 5) return set_error(CVLM_ERR_ARG, "tensor map: rank %d", spec.rank);
     for (int i = 0; i < spec.rank; ++i) {
         dims[i] = spec.dims[i];
         box[i] = spec.box[i];
