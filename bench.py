@@ -275,9 +275,22 @@ def run_ours(args):
     peaks = load_peaks()
     gemm_tflops = B * gemm_flops_per_image(cfg) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     step_tflops = B * cfg.flops_per_image() / (ms_total / K * 1e-3) / 1e12
+    # DRAM traffic per GEMM launch from the committed `ncu --set full` capture of this kernel (same batch)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_gemm_latest.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("batch") == B and args.model == "vit_h":
+                traffic = tj.get("mean_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm_tflops, "peak": peaks["sustained"],
-        "unit": "TFLOP/s", "frac": gemm_tflops / peaks["sustained"], "traffic": None,
+        "unit": "TFLOP/s", "frac": gemm_tflops / peaks["sustained"], "traffic": traffic,
+        "traffic_note": "mean dram__bytes_read+write per launch over the qkv/proj/lin1/lin2 launches of one block, "
+                        "ncu --set full at the same batch (profiles/ncu_gemm_latest.json); algorithmic bytes per "
+                        "launch are in DESIGN.md section 5",
         "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
         "launches_per_step": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
         "share_of_step": gemm_ms / (ms_total / K),

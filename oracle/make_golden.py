@@ -52,8 +52,31 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"encoder_{name}.npz"),
                             out=out.numpy(),
                             **{f"interm{i}": t.contiguous().numpy() for i, t in enumerate(interm)})
+    # downstream probe: the reference MaskDecoder_Edge on a seeded random embedding (pins the decoder oracle)
+    from oracle import mask_decoder_oracle as mdo
+    from oracle.ref_import import load_reference_decoder_modules
+    md, tr = load_reference_decoder_modules()
+    dec = md.MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                         transformer=tr.TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)).eval()
+    dsd = mdo.seeded_decoder_state(0)
+    dec.load_state_dict({k: v for k, v in dsd.items() if not k.startswith("probe.")}, strict=True)
+
+    def ref_decode(emb):
+        g = emb.shape[-1]
+        dense = dsd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(1, -1, g, g)
+        with torch.no_grad():
+            masks, _, _ = dec(image_embeddings=emb, interm_embeddings=[], image_pe=mdo.dense_pe(dsd, g),
+                              sparse_prompt_embeddings=dsd["probe.sparse"], dense_prompt_embeddings=dense,
+                              multimask_output=False)
+        return masks
+
+    emb = torch.randn(1, 256, 16, 16, generator=torch.Generator().manual_seed(0))
+    np.savez_compressed(os.path.join(GOLDEN, "decoder_small.npz"), emb=emb.numpy(), logits=ref_decode(emb).numpy())
     if args.full:
         out, interm = run_reference("vit_h", 1)
+        # full reference cascade tail on the reference embedding: low-res mask logits [1,1,256,256]
+        np.savez_compressed(os.path.join(GOLDEN, "decoder_vit_h_logits.npz"),
+                            logits=ref_decode(out).numpy().astype(np.float16))
         s, c = VITH_STRIDE, VITH_CH_STRIDE
         np.savez_compressed(os.path.join(GOLDEN, "encoder_vit_h_sub.npz"),
                             out=out[:, :, ::s, ::s].contiguous().numpy(),

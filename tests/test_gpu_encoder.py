@@ -93,6 +93,24 @@ def test_encoder_vit_h_matches_reference_golden():
     assert orc.rel_l2(outb[1:2], out) < BF16_TOL
 
 
+def test_downstream_mask_iou_vit_h():
+    """north_star gate: binary masks of the downstream MaskDecoder_Edge from OUR embedding vs from the
+    reference's embedding, IoU >= 0.99.  The golden logits come from the reference encoder + reference decoder
+    (oracle/make_golden.py); our side runs the CUDA encoder and the decoder oracle (the decoder only supports
+    batch 1, SURVEY.md 0.5, so it is applied per image)."""
+    from oracle import mask_decoder_oracle as mdo
+    cfg = PRESETS["vit_h"]
+    want_logits = torch.from_numpy(np.load(os.path.join(GOLDEN, "decoder_vit_h_logits.npz"))["logits"].astype(np.float32))
+    m = _encoder(cfg)
+    with torch.no_grad():
+        emb = m(seeded_images(cfg, 1).cuda())
+    got_logits = mdo.decode_mask_logits(mdo.seeded_decoder_state(0), emb.cpu())
+    got, want = mdo.binary_mask(got_logits, cfg.img_size), mdo.binary_mask(want_logits, cfg.img_size)
+    score = mdo.iou(got, want)
+    print(f"downstream mask IoU = {score:.5f} (positive fraction {float(want.float().mean()):.3f})")
+    assert score >= 0.99
+
+
 def test_state_dict_round_trip_and_reload():
     cfg = PRESETS["tiny"]
     m = _encoder(cfg, 0)

@@ -40,6 +40,21 @@ def main(out_path):
         print(name, json.dumps(r))
         del m
         torch.cuda.empty_cache()
+    # downstream probe: mask IoU of the reference decoder (oracle port) on our embedding vs the reference's
+    from oracle import mask_decoder_oracle as mdo
+    cfg = PRESETS["vit_h"]
+    m = build_encoder(cfg).eval()
+    m.load_state_dict(seeded_state_dict(cfg), strict=True)
+    m = m.cuda()
+    with torch.no_grad():
+        emb = m(seeded_images(cfg, 1).cuda())
+    want = torch.from_numpy(np.load(os.path.join(GOLDEN, "decoder_vit_h_logits.npz"))["logits"].astype(np.float32))
+    got = mdo.decode_mask_logits(mdo.seeded_decoder_state(0), emb.cpu())
+    rep["vit_h_downstream_mask_iou"] = mdo.iou(mdo.binary_mask(got, 1024), mdo.binary_mask(want, 1024))
+    rep["vit_h_downstream_logits_rel_l2"] = orc.rel_l2(got, want)
+    print("downstream mask IoU:", rep["vit_h_downstream_mask_iou"], "logits rel-L2:", rep["vit_h_downstream_logits_rel_l2"])
+    del m
+    torch.cuda.empty_cache()
     # how much does the cuFFT high-pass depend on the batch it is computed in?
     cfg = PRESETS["vit_h"]
     x = seeded_images(cfg, 2).cuda()
