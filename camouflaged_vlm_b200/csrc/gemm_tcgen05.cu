@@ -43,19 +43,22 @@ struct GemmEpi {
     int act_gelu;
 };
 
-// Exact-erf GELU (nn.GELU default, common.py:26).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7,
-// far below the bf16 rounding of the output) on two MUFU ops + 8 FMA instead of libdevice erff's
-// branchy ~30 instructions: the lin1 epilogue was the bottleneck of that GEMM (profiles/r1a).
+// Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
+// (|abs err of erf| <= 1.5e-7, far below the bf16 rounding of the output).  Written as
+//   gelu(x) = max(x, 0) - |x| * E,   E = 0.5 * poly(t) * t * exp(-z^2),  z = |x| / sqrt(2),  t = 1 / (1 + p z)
+// with the log2(e) of the exponential folded into z: 13 instructions, two of them MUFU (rcp, ex2), instead
+// of libdevice erff's branchy ~30 -- the lin1 epilogue was the bottleneck of that GEMM (profiles/r1a, r1e).
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = __expf(-z * z);
-    const float erf_abs = fmaf(-p * t, e, 1.0f);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float ax = fabsf(x);
+    const float zs = ax * 0.8493218002880191f;                 // z * sqrt(log2 e)
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, zs, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-zs * zs));
+    float p = fmaf(t, 0.5307027145f, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    return fmaf(-ax, p * t * e, fmaxf(x, 0.0f));
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)

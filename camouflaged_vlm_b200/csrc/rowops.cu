@@ -18,21 +18,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 // image_encoder.py:431, 444; eps bound by the caller, models/sam_maskdecoder_edge.py:129).
 // One warp per row, the row lives in registers, two-pass mean / biased variance like ATen.
 constexpr int LN_VMAX = 16;   // float4 per lane -> cols <= 2048
-template <bool kOutBf16>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, void* __restrict__ out,
-                                                        long long rows, int cols, float eps) {
+// NV > 0: cols == NV * 128 exactly (ViT-B/L/H widths and the 256-wide neck): fully unrolled, no guards,
+// few enough registers for 3 CTAs (24 warps) per SM.  NV == 0: generic width (cols % 4 == 0, <= 2048).
+template <bool kOutBf16, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 void* __restrict__ out, long long rows, int cols, float eps) {
+    constexpr int SLOTS = NV > 0 ? NV : LN_VMAX;
     const int lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int nvec = cols >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
-    float4 v[LN_VMAX];
+    float4 v[SLOTS];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_VMAX; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
         const int idx = lane + i * 32;
-        if (idx < nvec) {
+        if (NV > 0 || idx < nvec) {
             v[i] = __ldcs(xr + idx);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
@@ -40,9 +43,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float mean = warp_sum(s) / cols;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_VMAX; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
         const int idx = lane + i * 32;
-        if (idx < nvec) {
+        if (NV > 0 || idx < nvec) {
             const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
             q += (a * a + b * b) + (c * c + d * d);
         }
@@ -51,9 +54,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-    for (int i = 0; i < LN_VMAX; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
         const int idx = lane + i * 32;
-        if (idx < nvec) {
+        if (NV > 0 || idx < nvec) {
             const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
             float4 y;
             y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
@@ -70,17 +73,31 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+template <bool kOutBf16>
+static void layernorm_dispatch(const float* x, const float* gamma, const float* beta, void* out, long long rows, int cols,
+                               float eps, cudaStream_t stream) {
+    const int wpb = 8;
+    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+#define CVLM_LN(NV) layernorm_kernel<kOutBf16, NV><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, cols, eps)
+    switch (cols) {
+        case 256: CVLM_LN(2); break;
+        case 768: CVLM_LN(6); break;
+        case 1024: CVLM_LN(8); break;
+        case 1280: CVLM_LN(10); break;
+        default: CVLM_LN(0); break;
+    }
+#undef CVLM_LN
+}
+
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
                      int cols, float eps, cudaStream_t stream) {
     if (!x || !gamma || !beta || !out) return set_error(CVLM_ERR_ARG, "layernorm: null pointer");
     if (rows <= 0 || cols <= 0 || (cols & 3) || cols > LN_VMAX * 128)
         return set_error(CVLM_ERR_ARG, "layernorm: cols=%d must be a multiple of 4 and <= %d", cols, LN_VMAX * 128);
-    const int wpb = 8;
-    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
     if (out_bf16)
-        layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, cols, eps);
+        layernorm_dispatch<true>(x, gamma, beta, out, rows, cols, eps, stream);
     else
-        layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, rows, cols, eps);
+        layernorm_dispatch<false>(x, gamma, beta, out, rows, cols, eps, stream);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
