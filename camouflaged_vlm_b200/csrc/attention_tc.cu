@@ -111,7 +111,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(q_full, LOAD_BYTES);
             tma_load_3d(sQ, &tmQKV, q_full, 0, head, tok0 + qt * 128);
             if (HI) tma_load_3d(sQ + TC_TILE, &tmQKV, q_full, 64, head, tok0 + qt * 128);
@@ -151,7 +151,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idescS = umma_idesc_bf16(128, 128);
             constexpr uint32_t idescO = umma_idesc_bf16_bmn(128, HD);
             mbar_wait(q_full, 0);

@@ -124,7 +124,7 @@ attn_window_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(rel_full, (HI ? 4 : 2) * 32 * 128);
             tma_load_2d(sRel, &tmRelH, rel_full, 0, 0);
             tma_load_2d(sRel + 32 * 128, &tmRelW, rel_full, 0, 0);
@@ -155,7 +155,7 @@ attn_window_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idescT = umma_idesc_bf16(128, 64);
             constexpr uint32_t idescS = umma_idesc_bf16(128, WN_ROWS);
             constexpr uint32_t idescO = umma_idesc_bf16_bmn(128, HD);

@@ -54,8 +54,14 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
 int attention_global_tc_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
                                int head_dim, cudaStream_t stream);
 
+int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
+                                int head_dim, cudaStream_t stream);
+
 int attention_window_tc_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                                int heads, int head_dim, cudaStream_t stream);
+
+int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
+                                int heads, int head_dim, cudaStream_t stream);
 
 // ---- row kernels (rowops.cu)
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,

@@ -156,3 +156,21 @@ def test_attention(batch, grid, window, heads, hd):
     got = ops.attention(qkv, relh, relw, batch, grid, window, heads, hd).float()
     # bf16 P and bf16 output: ~2^-8 relative
     assert _rel(got, want) < 8e-3
+
+
+@pytest.mark.parametrize("window", [0, 14])
+@pytest.mark.parametrize("qscale", [3.0, 6.0])
+def test_attention_wide_logit_range(window, qscale):
+    """Peaked rows: logits spread over tens of log2 units, so the single-pass softmax of the tcgen05 kernels
+    has to raise its reference mid-row (the slow path) and must still match the fp32 restatement."""
+    batch, grid, heads, hd = 1, 64, 2, 80
+    d = heads * hd
+    s = window if window > 0 else grid
+    qkv = _randn(batch * grid * grid, 3 * d, seed=50, dtype=torch.bfloat16, scale=qscale)
+    qkv[:, 2 * d:] = _randn(batch * grid * grid, d, seed=51, dtype=torch.bfloat16, scale=0.8)   # keep V tame
+    relh = _randn(2 * s - 1, hd, seed=52, dtype=torch.bfloat16, scale=0.3)
+    relw = _randn(2 * s - 1, hd, seed=53, dtype=torch.bfloat16, scale=0.3)
+    want = cp.attention(qkv, relh, relw, batch, grid, window, heads, hd)
+    got = ops.attention(qkv, relh, relw, batch, grid, window, heads, hd).float()
+    assert torch.isfinite(got).all()
+    assert _rel(got, want) < 8e-3

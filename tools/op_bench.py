@@ -29,8 +29,9 @@ def main():
     rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device="cuda") * sc)
     a = rn(M, D).bfloat16()
     res = rn(M, D)
+    only_attn = len(sys.argv) > 2 and sys.argv[2] == "attn"
     print(f"batch {B}: M = {M}")
-    for name, n, k, kw in (("qkv", 3 * D, D, dict(out_dtype=torch.bfloat16)),
+    for name, n, k, kw in () if only_attn else (("qkv", 3 * D, D, dict(out_dtype=torch.bfloat16)),
                            ("proj", D, D, dict(residual=res)),
                            ("lin1", 4 * D, D, dict(out_dtype=torch.bfloat16, gelu=True)),
                            ("lin2", D, 4 * D, dict(residual=res))):
