@@ -10,15 +10,19 @@
 //
 // Persistent CTAs loop over (image, window, head) items; an item is two query tiles of 128 rows (tile 1
 // holds queries 128..195; it is skipped for bottom-edge windows where those are all padding).
-//   warp 0       TMA producer (Q double-buffered; K and V single slots, reloaded as soon as the MMAs that
-//                read them retire).
+//   warp 0       TMA producer (Q, K and V single slots, reloaded as soon as the MMAs that read them retire; the
+//                next item's S' cannot start before this item's epilogue anyway, so the loads are hidden).
 //   warp 1       MMA issuer.  The key tile K' has 256 rows: 196 keys, then rel_pos_h (27 rows) and rel_pos_w
 //                (27 rows) written once per CTA, so ONE tcgen05.mma chain  S' = Q K'^T  (M128 N256, K = 64 + 16)
 //                yields the logits (columns 0..195) and T_h / T_w = q . rel_pos (columns 196..249, unscaled q,
 //                image_encoder.py:618-619).  O = P V is a TS chain (P from TMEM, V MN-major, K = 208).
 //   warp 2       TMEM allocator: 512 columns = one 256-column S' region per query tile; bf16 P is written over
 //                the consumed S columns [0,104) and O lands in [112,192) of the same region.
-//   warps 4-7    softmax + epilogue of query tile 0, warps 8-11 of tile 1 (thread = query row).
+//   warps 4-7    softmax + epilogue of query tile 0, warps 8-11 of tile 1 (thread = query row).  A row needs
+//                th[ky] = T_h[qy - ky + 13] and tw[kx] = T_w[qx - kx + 13]: a per-thread dynamic index.  Each
+//                thread parks its 54 T values in a shared-memory scratch laid out [column][lane] (bank = lane,
+//                conflict free for any index) and reads the 28 it needs back -- registers cannot be indexed
+//                and local memory serialises 32 ways on divergent indices.
 // Softmax is single pass with a per-row reference that starts at the row's first logit and is only raised
 // when a 32-column chunk sums above 2^30 (see attention_tc2.cu); arithmetic is packed (FFMA2 / FADD2).
 #include "cvlm_internal.cuh"
@@ -32,9 +36,11 @@ constexpr int W2_TILE = W2_ROWS * 128;               // [208 rows x 64 bf16], 26
 constexpr int W2_SLOT = 2 * W2_TILE;                 // lo + hi
 constexpr int W2_KTILE = W2_KROWS * 128;             // [256 rows x 64 bf16], 32 KB
 constexpr int W2_OFF_V = 0;
-constexpr int W2_OFF_Q = W2_SLOT;                    // two Q slots; query tile 1 reads 48 rows past a slot's 208 (don't-care
-constexpr int W2_OFF_K = W2_OFF_Q + 2 * W2_SLOT;     // rows), so K' (lo + hi, 64 KB) follows the Q slots
-constexpr int W2_OFF_BAR = W2_OFF_K + 2 * W2_KTILE;
+constexpr int W2_OFF_Q = W2_SLOT;                    // query tile 1 reads 48 rows past the slot's 208 (don't-care rows),
+constexpr int W2_OFF_K = W2_OFF_Q + W2_SLOT;         // so K' (lo + hi, 64 KB) follows the Q slot
+constexpr int W2_OFF_STG = W2_OFF_K + 2 * W2_KTILE;  // T scratch: 7 active softmax warps x [54 columns][32 lanes] fp32
+constexpr int W2_STG_WARP = 54 * 128;
+constexpr int W2_OFF_BAR = W2_OFF_STG + 7 * W2_STG_WARP;
 constexpr int W2_SMEM = W2_OFF_BAR + 256 + 1024;
 static_assert(W2_SMEM <= 232448, "attention_tc_win2 shared memory");
 constexpr int W2_BOX_BYTES = 64 * W2_L * 2;          // bytes one TMA box delivers
@@ -133,10 +139,9 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sK = base + W2_OFF_K, sV = base + W2_OFF_V;
-    auto sQ = [&](int s) { return base + W2_OFF_Q + s * W2_SLOT; };
+    const uint32_t sQ = base + W2_OFF_Q;
     const uint32_t bars = base + W2_OFF_BAR;
-    auto q_full = [&](int s) { return bars + 8u * (0 + s); };
-    auto q_empty = [&](int s) { return bars + 8u * (2 + s); };
+    const uint32_t q_full = bars, q_empty = bars + 8u * 2;
     const uint32_t k_full = bars + 8u * 4, k_empty = bars + 8u * 5, v_full = bars + 8u * 6, v_empty = bars + 8u * 7;
     auto s_full = [&](int t) { return bars + 8u * (8 + t); };
     auto p_full = [&](int t) { return bars + 8u * (10 + t); };
@@ -181,9 +186,9 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
     fence_proxy_async_smem();
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
     if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(q_full(s), 1);
-            mbar_init(q_empty(s), 1);
             mbar_init(s_full(s), 1);
             mbar_init(p_full(s), 128);
             mbar_init(o_full(s), 1);
@@ -211,14 +216,12 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
             int n = 0;
             for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
                 const Win2Item w = decode(it);
-                const int qs = n & 1;
-                const uint32_t ph = static_cast<uint32_t>(n & 1);          // K / V: one slot, phase flips per item
-                const uint32_t qph = static_cast<uint32_t>((n >> 1) & 1);  // Q: two slots
+                const uint32_t ph = static_cast<uint32_t>(n & 1);          // one slot each: the phase flips per item
                 const int x0 = w.wx * W2_WS, y0 = w.wy * W2_WS;
-                mbar_wait(q_empty(qs), qph ^ 1u);
-                mbar_arrive_expect_tx(q_full(qs), LOAD_BYTES);
-                tma_load_5d(sQ(qs), &tmQKV, q_full(qs), 0, w.head, x0, y0, w.b);
-                if (HI) tma_load_5d(sQ(qs) + W2_TILE, &tmQKV, q_full(qs), 64, w.head, x0, y0, w.b);
+                mbar_wait(q_empty, ph ^ 1u);
+                mbar_arrive_expect_tx(q_full, LOAD_BYTES);
+                tma_load_5d(sQ, &tmQKV, q_full, 0, w.head, x0, y0, w.b);
+                if (HI) tma_load_5d(sQ + W2_TILE, &tmQKV, q_full, 64, w.head, x0, y0, w.b);
                 mbar_wait(k_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(k_full, LOAD_BYTES);
                 tma_load_5d(sK, &tmQKV, k_full, 0, heads + w.head, x0, y0, w.b);
@@ -238,8 +241,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
             uint32_t uses[2] = {0, 0};               // how many times tile t has been processed
             for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
                 const Win2Item w = decode(it);
-                const int qs = n & 1;
-                mbar_wait(q_full(qs), static_cast<uint32_t>((n >> 1) & 1));
+                mbar_wait(q_full, static_cast<uint32_t>(n & 1));
                 mbar_wait(k_full, static_cast<uint32_t>(n & 1));
                 tc_fence_after();
                 for (int t = 0; t < w.ntiles; ++t) {
@@ -248,14 +250,14 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                         tc_fence_after();
                     }
                     const uint32_t d = tmem_base + t * 256;
-                    const uint64_t q_lo = umma_desc_k_sw128(sQ(qs) + t * 128 * 128);
-                    const uint64_t q_hi = umma_desc_k_sw128(sQ(qs) + W2_TILE + t * 128 * 128);
+                    const uint64_t q_lo = umma_desc_k_sw128(sQ + t * 128 * 128);
+                    const uint64_t q_hi = umma_desc_k_sw128(sQ + W2_TILE + t * 128 * 128);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16_ss(d, q_lo + 2u * k, k_lo + 2u * k, idescS, k > 0);
                     if (HI) umma_bf16_ss(d, q_hi, k_hi, idescS, 1);
                     umma_commit(s_full(t));
                 }
-                umma_commit(q_empty(qs));
+                umma_commit(q_empty);
                 umma_commit(k_empty);
                 for (int t = 0; t < w.ntiles; ++t) {
                     mbar_wait(p_full(t), uses[t] & 1u);
@@ -286,6 +288,8 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
         const bool warp_active = t * 128 + (warp & 3) * 32 < W2_L;        // any query of the window in this warp
         const int qy = q_in_window ? l_q / W2_WS : 0, qx = q_in_window ? l_q - qy * W2_WS : 0;
         const uint64_t scale2 = f32x2_pack(scale_log2, scale_log2);
+        // this thread's column of the T scratch (warps of tile 1 use slots 4..6; the all-padding warp has none)
+        const uint32_t stg = base + W2_OFF_STG + (t * 4 + (warp & 3)) * W2_STG_WARP + lane * 4;
         uint32_t use = 0;
         for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
             const Win2Item w = decode(it);
@@ -295,23 +299,21 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
             float l = 1.f;
             if (warp_active) {
                 // ---- this row of T = q . [rel_pos_h ; rel_pos_w]: S' columns 192..255 hold keys 192..195, T_h, T_w
-                float trow[64];
                 uint32_t va[32], vb[32];
                 tmem_ld_32x32(t_s + 192, va);
-                tmem_ld_wait(va);
                 tmem_ld_32x32(t_s + 224, vb);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) trow[i] = __uint_as_float(va[i]);
-                uint32_t tail[4] = {va[0], va[1], va[2], va[3]};           // logits of keys 192..195
+                tmem_ld_wait(va);
                 tmem_ld_wait(vb);
-                tmem_ld_32x32(t_s, va);                                    // chunk 0 in flight
+                const uint32_t tail[4] = {va[0], va[1], va[2], va[3]};     // logits of keys 192..195
 #pragma unroll
-                for (int i = 0; i < 32; ++i) trow[32 + i] = __uint_as_float(vb[i]);
+                for (int c = 0; c < 54; ++c)                               // T column c = S' column 196 + c
+                    st_shared_b32(stg + c * 128, c < 28 ? va[4 + c] : vb[c - 28]);
+                tmem_ld_32x32(t_s, va);                                    // chunk 0 in flight
                 float th[W2_WS], tw[W2_WS];
 #pragma unroll
                 for (int k = 0; k < W2_WS; ++k) {
-                    th[k] = trow[(W2_REL_H - 192) + qy + 13 - k] * kLog2eW2;   // rel_h[q, ky] = T_h[q][qy - ky + 13]
-                    tw[k] = trow[(W2_REL_W - 192) + qx + 13 - k] * kLog2eW2;   // rel_w[q, kx] = T_w[q][qx - kx + 13]
+                    th[k] = ld_shared_f32(stg + (qy + 13 - k) * 128) * kLog2eW2;        // rel_h[q, ky] = T_h[q][qy - ky + 13]
+                    tw[k] = ld_shared_f32(stg + (27 + qx + 13 - k) * 128) * kLog2eW2;   // rel_w[q, kx] = T_w[q][qx - kx + 13]
                 }
                 uint64_t tw2[7], thm2[W2_WS];
 #pragma unroll
@@ -356,37 +358,36 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 const float inv = 1.0f / l;
                 __nv_bfloat16* orow = out + ((static_cast<long long>(w.b) * G + gy) * G + gx) * D + w.head * HD;
                 const uint32_t t_o = t_s + W2_COL_O;
-                uint32_t v[32];
+                uint32_t o0[32], o1[32], o2[16];
+                tmem_ld_32x32(t_o, o0);
+                tmem_ld_32x32(t_o + 32, o1);
+                if (HI) tmem_ld_32x16(t_o + 64, o2);
+                tmem_ld_wait(o0);
+                tmem_ld_wait(o1);
+                if (HI) tmem_ld_wait16(o2);
+                if (store) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld_32x32(t_o + c * 32, v);
-                    tmem_ld_wait(v);
-                    if (store) {
+                    for (int i = 0; i < 32; i += 16) {
+                        uint32_t pk[8];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 pk;
-                            pk.x = pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-                            pk.y = pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                            pk.z = pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-                            pk.w = pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-                            *reinterpret_cast<uint4*>(orow + c * 32 + i) = pk;
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            pk[e] = pack_bf16(__uint_as_float(o0[i + 2 * e]) * inv, __uint_as_float(o0[i + 2 * e + 1]) * inv);
+                        st_global_v8(orow + i, pk);
                     }
-                }
-                if (HI) {
-                    uint32_t w16[16];
-                    tmem_ld_32x16(t_o + 64, w16);
-                    tmem_ld_wait16(w16);
-                    if (store) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 8) {
-                            uint4 pk;
-                            pk.x = pack_bf16(__uint_as_float(w16[i]) * inv, __uint_as_float(w16[i + 1]) * inv);
-                            pk.y = pack_bf16(__uint_as_float(w16[i + 2]) * inv, __uint_as_float(w16[i + 3]) * inv);
-                            pk.z = pack_bf16(__uint_as_float(w16[i + 4]) * inv, __uint_as_float(w16[i + 5]) * inv);
-                            pk.w = pack_bf16(__uint_as_float(w16[i + 6]) * inv, __uint_as_float(w16[i + 7]) * inv);
-                            *reinterpret_cast<uint4*>(orow + 64 + i) = pk;
-                        }
+                    for (int i = 0; i < 32; i += 16) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            pk[e] = pack_bf16(__uint_as_float(o1[i + 2 * e]) * inv, __uint_as_float(o1[i + 2 * e + 1]) * inv);
+                        st_global_v8(orow + 32 + i, pk);
+                    }
+                    if (HI) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            pk[e] = pack_bf16(__uint_as_float(o2[2 * e]) * inv, __uint_as_float(o2[2 * e + 1]) * inv);
+                        st_global_v8(orow + 64, pk);
                     }
                 }
             }

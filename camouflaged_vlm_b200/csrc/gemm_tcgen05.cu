@@ -61,6 +61,30 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-ax, p * t * e, fmaxf(x, 0.0f));
 }
 
+// The same on a pair (FFMA2 / FMUL2): 9 issue slots per element instead of 14 -- the lin1 epilogue is issue bound
+// (profiles/ncu_gemm_r1e: 55 % issue-active with two epilogue warps per scheduler).  The polynomial carries the
+// minus sign of "- |x| * E".
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+    float x0, x1;
+    f32x2_unpack(x2, x0, x1);
+    const uint64_t ax2 = f32x2_pack(fabsf(x0), fabsf(x1));
+    const uint64_t zs2 = f32x2_mul(ax2, f32x2_pack(0.8493218002880191f, 0.8493218002880191f));
+    float a0, a1, z0, z1;
+    f32x2_unpack(f32x2_fma(zs2, f32x2_pack(0.2727374808792225f, 0.2727374808792225f), f32x2_pack(1.0f, 1.0f)), a0, a1);
+    f32x2_unpack(f32x2_mul(zs2, zs2), z0, z1);
+    float t0, t1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+    const float e0 = ex2_approx(-z0), e1 = ex2_approx(-z1);
+    const uint64_t t2 = f32x2_pack(t0, t1);
+    uint64_t p = f32x2_fma(t2, f32x2_pack(-0.5307027145f, -0.5307027145f), f32x2_pack(0.7265760135f, 0.7265760135f));
+    p = f32x2_fma(p, t2, f32x2_pack(-0.7107068705f, -0.7107068705f));
+    p = f32x2_fma(p, t2, f32x2_pack(0.142248368f, 0.142248368f));
+    p = f32x2_fma(p, t2, f32x2_pack(-0.127414796f, -0.127414796f));
+    p = f32x2_mul(f32x2_mul(p, t2), f32x2_pack(e0, e1));
+    return f32x2_fma(ax2, p, f32x2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -239,37 +263,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         }
                     }
                 } else {
+                    // bf16 output (qkv, lin1, adapter): 8 columns per lane, packed fp32 pairs all the way
                     const int c8 = lane & 3, rsub = lane >> 2;
                     const int col = col0 + c8 * 8;
                     const bool col_ok = col < N;           // N % 8 == 0
-                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    uint64_t bb[4] = {0ull, 0ull, 0ull, 0ull};
                     if (bias && col_ok) {
-                        b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                        b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                        bb[0] = f32x2_pack(b0.x, b0.y); bb[1] = f32x2_pack(b0.z, b0.w);
+                        bb[2] = f32x2_pack(b1.x, b1.y); bb[3] = f32x2_pack(b1.z, b1.w);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = 8 * i + rsub;
                         const int row = row_base + r;
-                        float4 x0 = ld_shared_f4(stg + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
-                        float4 x1 = ld_shared_f4(stg + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
+                        const float4 x0 = ld_shared_f4(stg + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
+                        const float4 x1 = ld_shared_f4(stg + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
                         if (row < M && col_ok) {
-                            x0.x += b0.x; x0.y += b0.y; x0.z += b0.z; x0.w += b0.w;
-                            x1.x += b1.x; x1.y += b1.y; x1.z += b1.z; x1.w += b1.w;
+                            uint64_t y[4] = {f32x2_add(f32x2_pack(x0.x, x0.y), bb[0]), f32x2_add(f32x2_pack(x0.z, x0.w), bb[1]),
+                                             f32x2_add(f32x2_pack(x1.x, x1.y), bb[2]), f32x2_add(f32x2_pack(x1.z, x1.w), bb[3])};
                             if (ep.act_gelu) {
-                                x0.x = gelu_erf(x0.x); x0.y = gelu_erf(x0.y); x0.z = gelu_erf(x0.z); x0.w = gelu_erf(x0.w);
-                                x1.x = gelu_erf(x1.x); x1.y = gelu_erf(x1.y); x1.z = gelu_erf(x1.z); x1.w = gelu_erf(x1.w);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
                             }
                             if (ep.residual) {
                                 const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
                                 const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                                 const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col + 4);
-                                x0.x += r0.x; x0.y += r0.y; x0.z += r0.z; x0.w += r0.w;
-                                x1.x += r1.x; x1.y += r1.y; x1.z += r1.z; x1.w += r1.w;
+                                y[0] = f32x2_add(y[0], f32x2_pack(r0.x, r0.y)); y[1] = f32x2_add(y[1], f32x2_pack(r0.z, r0.w));
+                                y[2] = f32x2_add(y[2], f32x2_pack(r1.x, r1.y)); y[3] = f32x2_add(y[3], f32x2_pack(r1.z, r1.w));
                             }
                             uint4 pk;
-                            pk.x = pack_bf16(x0.x, x0.y); pk.y = pack_bf16(x0.z, x0.w);
-                            pk.z = pack_bf16(x1.x, x1.y); pk.w = pack_bf16(x1.z, x1.w);
+                            float lo, hi;
+                            f32x2_unpack(y[0], lo, hi); pk.x = pack_bf16(lo, hi);
+                            f32x2_unpack(y[1], lo, hi); pk.y = pack_bf16(lo, hi);
+                            f32x2_unpack(y[2], lo, hi); pk.z = pack_bf16(lo, hi);
+                            f32x2_unpack(y[3], lo, hi); pk.w = pack_bf16(lo, hi);
                             *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = pk;
                         }
                     }
