@@ -14,6 +14,8 @@
 // The accumulator double buffer lets the MMA of tile i+1 overlap the epilogue of tile i.
 // Operands are K-major in global memory (activations [M,K], weights [N,K]); ragged M/N/K edges
 // are handled by TMA out-of-bounds zero fill plus predicated stores.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -22,7 +24,7 @@
 
 namespace cvlm {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, STAGES_PAIR = 6, UMMA_K = 16;
 constexpr int A_STAGE = BM * BK * 2;     // 16 KB
 constexpr int B_STAGE = BN * BK * 2;     // 32 KB
 constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
@@ -30,7 +32,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_STAGING = EPI_WARPS * 4096;   // one 32x32 fp32 transpose tile per epilogue warp
 constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
-static_assert(GEMM_SMEM <= 232448, "exceeds the 227 KB shared memory of one CTA");
+constexpr int GEMM_SMEM_PAIR = STAGES_PAIR * (A_STAGE + B_STAGE / 2) + EPI_STAGING + 1024 + 256;
+static_assert(GEMM_SMEM <= 232448 && GEMM_SMEM_PAIR <= 232448, "exceeds the 227 KB shared memory of one CTA");
 
 struct GemmEpi {
     const float* bias;
@@ -85,27 +88,43 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
     return f32x2_fma(ax2, p, f32x2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
 }
 
+// PAIR = false: one CTA per 128 x 256 tile (small problems).
+// PAIR = true : a cluster of two CTAs (one TPC) per 256 x 256 tile, tcgen05.mma.cta_group::2.  Each CTA stages its own
+//   128 rows of A and HALF of the B tile (128 of the 256 weight rows), so the tensor core's shared-memory operand
+//   traffic per CTA drops from 48 KB to 32 KB per k-block -- the 1-CTA kernel keeps the SM's shared-memory pipe
+//   94 % busy on the qkv GEMM (profiles/ncu_gemm_r1e) and that, not the tensor pipe, was its ceiling.  The leader
+//   CTA (rank 0) issues the MMAs for both; TMA completions of both CTAs land on the leader's "full" barrier,
+//   tcgen05.commit multicasts "empty" / "accumulator full" to both CTAs, and the epilogue warps of both CTAs
+//   hand the accumulator back by arriving on the leader's "accumulator empty" barrier.
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                          int kblocks1, int kblocks2, int M, int N, int tiles_m, int tiles_n, GemmEpi ep) {
+    constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
+    constexpr int B_BYTES = PAIR ? B_STAGE / 2 : B_STAGE;      // bytes of B this CTA stages per k-block
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base;
-    const uint32_t sB = base + STAGES * A_STAGE;
-    const uint32_t staging = sB + STAGES * B_STAGE;
+    const uint32_t sB = base + NSTAGE * A_STAGE;
+    const uint32_t staging = sB + NSTAGE * B_BYTES;
     const uint32_t bars = staging + EPI_STAGING;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = kblocks1 + kblocks2;
     const int num_tiles = tiles_m * tiles_n;
+    // work unit of this CTA (PAIR: of this cluster) and its stride over the tile list
+    const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+    const int first_tile = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    const int tile_stride = PAIR ? gridDim.x >> 1 : gridDim.x;
+    constexpr int TILE_M = PAIR ? 2 * BM : BM;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA1);
@@ -116,22 +135,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), EPI_WARPS);
+            mbar_init(tempty_bar(a), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_pair(tmem_slot, TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // peer barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -140,16 +164,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+                const int m0 = (tile / tiles_n) * TILE_M + cta_rank * BM;
+                const int n0 = (tile % tiles_n) * BN + (PAIR ? cta_rank * (BN / 2) : 0);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), A_STAGE + B_STAGE);
                     const bool second = kb >= kblocks1;
                     const int kc = (second ? kb - kblocks1 : kb) * BK;
-                    tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), kc, m0);
-                    tma_load_2d(sB + stage * B_STAGE, second ? &tmB2 : &tmB1, full_bar(stage), kc, n0);
-                    if (++stage == STAGES) {
+                    if (PAIR) {
+                        // the leader arms its barrier with the bytes of both CTAs; both CTAs' copies complete on it
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (A_STAGE + B_BYTES));
+                        const uint32_t lead_bar = full_bar(stage) & kPeerBitMask;
+                        tma_load_2d_pair(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, lead_bar, kc, m0);
+                        tma_load_2d_pair(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, lead_bar, kc, n0);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), A_STAGE + B_BYTES);
+                        tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), kc, m0);
+                        tma_load_2d(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, full_bar(stage), kc, n0);
+                    }
+                    if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -157,13 +190,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single lane) =====================
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        // ===================== MMA issuer (single lane; PAIR: of the leader CTA only) =====================
+        if (cta_rank == 0 && elect_one_sync()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
                 const int acc = iter & 1;
                 mbar_wait(tempty_bar(acc), (((iter >> 1) & 1) ^ 1u));   // epilogue drained this accumulator
                 tc_fence_after();
@@ -172,15 +205,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_k_sw128(sA + stage * A_STAGE);
-                    const uint64_t bdesc = umma_desc_k_sw128(sB + stage * B_STAGE);
+                    const uint64_t bdesc = umma_desc_k_sw128(sB + stage * B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B along K inside the 128 B swizzle span: +2 in 16-byte units
-                        umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+                        if (PAIR) umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+                        else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
-                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
-                    if (++stage == STAGES) {
+                    if (PAIR) {
+                        umma_commit_pair(empty_bar(stage));                // smem slot free in BOTH CTAs
+                        if (kb == kblocks - 1) umma_commit_pair(tfull_bar(acc));
+                    } else {
+                        umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                        if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+                    }
+                    if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -200,9 +239,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         const uint32_t stg = staging + ew * 4096;
         const float* __restrict__ bias = ep.bias;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
             const int acc = iter & 1;
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int m0 = (tile / tiles_n) * TILE_M + cta_rank * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
             tc_fence_after();
             const int row_base = m0 + quad * 32;
@@ -233,7 +272,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's barrier
+                        else mbar_arrive(tempty_bar(acc));
+                    }
                 }
                 if (col0 >= N || row_base >= M) continue;   // warp-uniform
 #pragma unroll
@@ -310,10 +352,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
     }
     // ---- teardown
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -407,27 +450,54 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)))
         return set_error(CVLM_ERR_ARG, "gemm: epilogue pointers / strides must allow 16-byte vectors");
     const int brows = a.b_rows > 0 ? a.b_rows : a.n;
+    // 256 x 256 cluster tiles whenever they fill the machine; CVLM_GEMM_MODE=1cta / pair forces one kernel
+    // (read per call: the parity tests flip it to cover both kernels on every shape).
+    const char* mode = getenv("CVLM_GEMM_MODE");
+    const int pair_tiles = ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
+    const bool pair = mode && mode[0] == 'p' ? true : mode && mode[0] == '1' ? false : pair_tiles >= num_sms() / 2;
+    const int b_box = pair ? BN / 2 : BN;
     CUtensorMap tA1, tB1, tA2, tB2;
     CVLM_TRY(make_tensor_map(&tA1, a.a1, a.m, a.k1, a.lda1, BM));
-    CVLM_TRY(make_tensor_map(&tB1, a.b1, brows, a.k1, a.ldb1, BN));
+    CVLM_TRY(make_tensor_map(&tB1, a.b1, brows, a.k1, a.ldb1, b_box));
     if (a.k2 > 0) {
         CVLM_TRY(make_tensor_map(&tA2, a.a2, a.m, a.k2, a.lda2, BM));
-        CVLM_TRY(make_tensor_map(&tB2, a.b2, brows, a.k2, a.ldb2, BN));
+        CVLM_TRY(make_tensor_map(&tB2, a.b2, brows, a.k2, a.ldb2, b_box));
     } else {
         tA2 = tA1;
         tB2 = tB1;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAIR));
         attr_set = true;
     }
-    const int tiles_m = (a.m + BM - 1) / BM, tiles_n = (a.n + BN - 1) / BN;
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu};
-    const int grid = tiles_m * tiles_n < num_sms() ? tiles_m * tiles_n : num_sms();
-    gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, tiles_m,
-                                                                      tiles_n, ep);
+    const int tiles_n = (a.n + BN - 1) / BN;
+    if (pair) {
+        const int tiles_m = (a.m + 2 * BM - 1) / (2 * BM);
+        const int clusters = tiles_m * tiles_n < num_sms() / 2 ? tiles_m * tiles_n : num_sms() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = GEMM_SMEM_PAIR;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVLM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<true>, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, tiles_m,
+                                     tiles_n, ep));
+    } else {
+        const int tiles_m = (a.m + BM - 1) / BM;
+        const int grid = tiles_m * tiles_n < num_sms() ? tiles_m * tiles_n : num_sms();
+        gemm_bf16_tcgen05_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n,
+                                                                             tiles_m, tiles_n, ep);
+    }
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }

@@ -71,8 +71,15 @@ GEMM_SHAPES = [
 ]
 
 
+@pytest.fixture(params=["1cta", "pair"])
+def gemm_mode(request, monkeypatch):
+    """Run a GEMM test through both kernels: one CTA per 128x256 tile, and CTA pairs (cta_group::2) per 256x256."""
+    monkeypatch.setenv("CVLM_GEMM_MODE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-def test_gemm_plain(m, n, k):
+def test_gemm_plain(m, n, k, gemm_mode):
     a = _randn(m, k, seed=20, dtype=torch.bfloat16)
     b = _randn(n, k, seed=21, dtype=torch.bfloat16, scale=0.05)
     want = a.float() @ b.float().t()
@@ -83,7 +90,7 @@ def test_gemm_plain(m, n, k):
     assert _rel(got16.float(), want) < 4e-3
 
 
-def test_gemm_epilogues():
+def test_gemm_epilogues(gemm_mode):
     m, n, k = 512, 512, 320
     a = _randn(m, k, seed=22, dtype=torch.bfloat16)
     b = _randn(n, k, seed=23, dtype=torch.bfloat16, scale=0.05)
@@ -103,7 +110,7 @@ def test_gemm_epilogues():
     assert _rel(ops.gemm_bf16(a, b, bias=bias, residual=pos, res_row_mod=128), want) < 1e-5
 
 
-def test_gemm_two_k_segments_and_strided_operands():
+def test_gemm_two_k_segments_and_strided_operands(gemm_mode):
     m, n, k1, rp, depth = 640, 1280, 512, 40, 4
     a1 = _randn(m, k1, seed=27, dtype=torch.bfloat16)
     b1 = _randn(n, k1, seed=28, dtype=torch.bfloat16, scale=0.05)
