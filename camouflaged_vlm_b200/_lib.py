@@ -13,6 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libcvlm_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 MAX_DEPTH = 64
+STAT_GROUP_COLS = 128     # include/cvlm.h CVLM_STAT_GROUP_COLS
 PROF_KINDS = ("gemm_qkv", "gemm_proj", "gemm_lin1", "gemm_lin2", "gemm_other", "attn_window", "attn_global",
               "layernorm", "other")
 
@@ -69,6 +70,12 @@ _SIGS = {
                                     C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                     C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "cvlm_op_gemm_bf16_ln": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                       C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                       C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvlm_op_ln_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p]),
     "cvlm_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,

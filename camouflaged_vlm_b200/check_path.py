@@ -97,6 +97,16 @@ def attention(qkv, relh, relw, batch, g, window, heads, hd):
     return o[:, :g, :g, :].reshape(batch * g * g, d)
 
 
+def gemm_ln(x, w_scaled, colsum, bias, eps, gelu=False):
+    """LayerNorm folded around a GEMM the way the CUDA epilogue does it (packing.py):
+    rstd * (x W'^T - mu * colsum) + bias  ==  LN(x; gamma, beta) W^T + b."""
+    mu = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mu * mu
+    rstd = torch.rsqrt(var.clamp_min(0) + eps)
+    y = rstd * (x.float() @ w_scaled.float().t() - mu * colsum[None, :]) + bias[None, :]
+    return F.gelu(y) if gelu else y
+
+
 def layernorm2d_nchw(x, w, b, batch, tokens, eps):
     y = F.layer_norm(x, (x.shape[-1],), w, b, eps)
     return y.reshape(batch, tokens, -1).permute(0, 2, 1).contiguous()
@@ -127,8 +137,7 @@ def encoder_forward_check(p: Dict[str, torch.Tensor], cfg: EncoderConfig, images
     interms: List[torch.Tensor] = []
     for i in range(depth):
         o = f"blk.{i}."
-        a = F.layer_norm(x, (D,), p[o + "ln1.w"], p[o + "ln1.b"], ln_eps)
-        qkv = gemm(a, p[o + "qkv.w"], bias=p[o + "qkv.b"])
+        qkv = gemm_ln(x, p[o + "qkv.w"], p[o + "qkv.c"], p[o + "qkv.b"], ln_eps)
         a = attention(qkv, p[o + "relh"], p[o + "relw"], batch, g, cfg.block_window(i), cfg.num_heads, cfg.head_dim)
         x = gemm(a, p[o + "proj.w"], bias=p[o + "proj.b"], residual=x)
         a = F.layer_norm(x, (D,), p[o + "ln2.w"], p[o + "ln2.b"], ln_eps)

@@ -420,17 +420,13 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     if (p.S > 64) return set_error(CVLM_ERR_UNSUPPORTED, "attention: window / grid side > 64 tokens");
     if (static_cast<long long>(batch) * p.nW * p.nW > 65535)
         return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch * windows exceeds grid.z; split the batch");
-    // 64x64 global blocks run on the tcgen05 kernel (attention_tc.cu); CVLM_ATTN_LEGACY=1 forces the
-    // mma.sync kernel below (A/B comparisons, bisecting).
+    // 64x64 global blocks and 14x14 windows run on the tcgen05 kernels (attention_tc2.cu, attention_tc_win2.cu);
+    // CVLM_ATTN_LEGACY=1 forces the mma.sync kernel below (A/B comparisons, bisecting).
     static const bool legacy = getenv("CVLM_ATTN_LEGACY") != nullptr && getenv("CVLM_ATTN_LEGACY")[0] == '1';
-    // CVLM_ATTN_GEN1=1 selects the first-generation tcgen05 kernels (one query tile per CTA).
-    static const bool gen1 = getenv("CVLM_ATTN_GEN1") != nullptr && getenv("CVLM_ATTN_GEN1")[0] == '1';
     if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80))
-        return gen1 ? attention_global_tc_launch(qkv, out, relh, relw, batch, heads, head_dim, stream)
-                    : attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream);
+        return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream);
     if (!legacy && window == 14 && (head_dim == 64 || head_dim == 80))
-        return gen1 ? attention_window_tc_launch(qkv, out, relh, relw, batch, grid_side, heads, head_dim, stream)
-                    : attention_window_tc2_launch(qkv, out, relh, relw, batch, grid_side, heads, head_dim, stream);
+        return attention_window_tc2_launch(qkv, out, relh, relw, batch, grid_side, heads, head_dim, stream);
     const bool aligned = (p.S == ATT_BK);
     if (head_dim == 80)
         return aligned ? launch_attention<80, true>(p, batch, stream) : launch_attention<80, false>(p, batch, stream);

@@ -447,6 +447,12 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
     CVLM_TRY(make_tensor_map_bf16(&tw, r));
     auto kern = attn_global_tc2_kernel<HD, POLY>;
     CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    {   // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
+        cudaFuncAttributes fa;
+        CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
+        if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
+            return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+    }
     dim3 grid(16, heads, batch);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eG2;
     kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2);

@@ -421,6 +421,12 @@ static int launch_window_tc2(const void* qkv, void* out, const void* relh, const
         return set_error(CVLM_ERR_ARG, "attention: rel-pos tables must be 16-byte aligned");
     auto kern = attn_window_tc2_kernel<HD>;
     CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM));
+    {   // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
+        cudaFuncAttributes fa;
+        CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
+        if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
+            return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc_win2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+    }
     const int items = batch * nW * nW * heads;
     int sms = 148;
     {

@@ -44,6 +44,17 @@ struct GemmArgs {
     long long ldo = 0;
     int out_bf16 = 0;
     int act_gelu = 0;
+    // LayerNorm folded around the GEMMs.  nn.LayerNorm (image_encoder.py:430-446 norm1 / norm2) sits between a GEMM
+    // that writes the fp32 residual stream and a GEMM that reads its normalised bf16 copy.  Instead of a separate
+    // pass over x, the PRODUCER (fp32 path) also stores bf16(x) and, per row and column group, (sum x, sum x^2);
+    // ln_finalize turns those into (rstd, -mean * rstd) per row; the CONSUMER runs on the raw bf16(x) with gamma
+    // folded into its weights and applies
+    //     out = rstd * (acc - mean * colsum) + bias,   colsum[n] = sum_k W'[n, k],  bias = W beta + b
+    // in its epilogue.  Each partial has exactly one writer, so results do not depend on scheduling.
+    void* copy_bf16 = nullptr;  long long ldc = 0;       // producer: bf16 copy of out (must not alias a1 / a2)
+    float* stat_out = nullptr;  int stat_groups = 0;     // producer: fp32 [m, stat_groups, 2], stat_groups = ceil(n / CVLM_STAT_GROUP_COLS)
+    const float* ln_rows = nullptr;                      // consumer: fp32 [m, 2] = (rstd, -mean * rstd) of the A rows
+    const float* ln_colsum = nullptr;                    // consumer: fp32 [n]
 };
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
@@ -51,14 +62,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                      int window, int heads, int head_dim, cudaStream_t stream);
 
-int attention_global_tc_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                               int head_dim, cudaStream_t stream);
-
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
                                 int head_dim, cudaStream_t stream);
-
-int attention_window_tc_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                               int heads, int head_dim, cudaStream_t stream);
 
 int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                                 int heads, int head_dim, cudaStream_t stream);
@@ -66,6 +71,8 @@ int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, co
 // ---- row kernels (rowops.cu)
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
                      int cols, float eps, cudaStream_t stream);
+int ln_finalize_launch(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
+                       cudaStream_t stream);
 int cast_bf16_launch(const float* x, void* out, long long n, cudaStream_t stream);
 int im2col_patch_launch(const float* img, void* out, int batch, int chans, int img_size, int patch,
                         cudaStream_t stream);

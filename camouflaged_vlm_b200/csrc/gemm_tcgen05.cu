@@ -27,8 +27,12 @@ namespace cvlm {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, STAGES_PAIR = 6, UMMA_K = 16;
 constexpr int A_STAGE = BM * BK * 2;     // 16 KB
 constexpr int B_STAGE = BN * BK * 2;     // 32 KB
-constexpr int GEMM_THREADS = 384;        // 4 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;             // (16 warps / 5 stages measured slower on every GEMM: spills + a shallower ring)
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;   // 4 control warps + the epilogue warps
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);       // accumulator columns per epilogue warp (64)
+constexpr int EPI_CHUNKS = EPI_COLS / 32;
+static_assert(EPI_COLS == CVLM_STAT_GROUP_COLS, "row statistics are written per epilogue warp");
+
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_STAGING = EPI_WARPS * 4096;   // one 32x32 fp32 transpose tile per epilogue warp
 constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) + EPI_STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -44,6 +48,14 @@ struct GemmEpi {
     long long ldo;
     int out_bf16;
     int act_gelu;
+    // LayerNorm folded around the GEMMs (see GemmArgs): producer side ...
+    __nv_bfloat16* copy_bf16;     // fp32 path: also store bf16(out) here (the next GEMM's A operand), row stride ldc
+    long long ldc;
+    float2* stat_out;             // fp32 path: per (row, column group) partial (sum, sum of squares) of out
+    int stat_groups;
+    // ... and consumer side
+    const float2* ln_rows;        // bf16 path: (rstd, -mean * rstd) of this GEMM's A rows (ln_finalize_kernel)
+    const float* ln_colsum;       // [n] sum_k B[n, k]
 };
 
 // Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
@@ -235,22 +247,53 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         // 8 lanes x 16 B = one full 128-byte line of the fp32 output / residual per row.
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
-        const int half = ew >> 2;           // which 128 of the 256 accumulator columns
+        const int half = ew >> 2;           // which EPI_COLS of the 256 accumulator columns
         const uint32_t stg = staging + ew * 4096;
         const float* __restrict__ bias = ep.bias;
         int iter = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
             const int acc = iter & 1;
             const int m0 = (tile / tiles_n) * TILE_M + cta_rank * BM, n0 = (tile % tiles_n) * BN;
+            const int row_base = m0 + quad * 32;
+            // LayerNorm of the A rows, applied to the accumulator (GemmArgs::ln_stat): this lane's 4 rows of the
+            // bf16 path.  out = rstd * (acc - mu * colsum) + bias  ==  LN(x) * W^T + b  with gamma folded into W.
+            float ln_rs[4] = {1.f, 1.f, 1.f, 1.f}, ln_nm[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ep.ln_rows != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = row_base + 8 * i + (lane >> 2);
+                    if (row < M) {
+                        const float2 rn = __ldg(ep.ln_rows + row);
+                        ln_rs[i] = rn.x;
+                        ln_nm[i] = rn.y;
+                    }
+                }
+            }
+            float st1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
             tc_fence_after();
-            const int row_base = m0 + quad * 32;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = n0 + half * 128 + c * 32;
+            for (int c = 0; c < EPI_CHUNKS; ++c) {
+                const int col0 = n0 + half * EPI_COLS + c * 32;
                 // fp32 path: issue the chunk's 8 residual loads first, as one batch.  out may alias residual
                 // (in-place shortcut add), so loads interleaved with the stores below would be serialised
                 // behind them by the compiler and expose a full memory latency per row group.
+                // bf16 path: this lane's 8 bias / column-sum values, requested before the TMEM load and the transpose
+                // so that their latency is off the critical path
+                float4 pb0 = make_float4(0.f, 0.f, 0.f, 0.f), pb1 = pb0, pc0 = pb0, pc1 = pb0;
+                if (ep.out_bf16) {
+                    const int col = col0 + (lane & 3) * 8;
+                    if (col < N) {
+                        if (bias) {
+                            pb0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                            pb1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                        }
+                        if (ep.ln_rows != nullptr) {
+                            pc0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col));
+                            pc1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + 4));
+                        }
+                    }
+                }
                 float4 rr[8];
                 const bool use_res = ep.residual != nullptr && !ep.out_bf16;
                 if (use_res) {
@@ -266,9 +309,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     }
                 }
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128 + c * 32, v);
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * EPI_COLS + c * 32, v);
                 tmem_ld_wait(v);
-                if (c == 3) {
+                if (c == EPI_CHUNKS - 1) {
                     // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -302,6 +345,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
                             }
                             *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = x;
+                            if (ep.copy_bf16 != nullptr) {
+                                uint2 pk;
+                                pk.x = pack_bf16(x.x, x.y);
+                                pk.y = pack_bf16(x.z, x.w);
+                                *reinterpret_cast<uint2*>(ep.copy_bf16 + static_cast<long long>(row) * ep.ldc + col) = pk;
+                            }
+                            if (ep.stat_out != nullptr) {
+                                st1[i] += (x.x + x.y) + (x.z + x.w);
+                                st2[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+                            }
                         }
                     }
                 } else {
@@ -309,13 +362,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     const int c8 = lane & 3, rsub = lane >> 2;
                     const int col = col0 + c8 * 8;
                     const bool col_ok = col < N;           // N % 8 == 0
-                    uint64_t bb[4] = {0ull, 0ull, 0ull, 0ull};
-                    if (bias && col_ok) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-                        bb[0] = f32x2_pack(b0.x, b0.y); bb[1] = f32x2_pack(b0.z, b0.w);
-                        bb[2] = f32x2_pack(b1.x, b1.y); bb[3] = f32x2_pack(b1.z, b1.w);
-                    }
+                    const bool use_ln = ep.ln_rows != nullptr;
+                    uint64_t bb[4], cs[4];
+                    bb[0] = f32x2_pack(pb0.x, pb0.y); bb[1] = f32x2_pack(pb0.z, pb0.w);
+                    bb[2] = f32x2_pack(pb1.x, pb1.y); bb[3] = f32x2_pack(pb1.z, pb1.w);
+                    cs[0] = f32x2_pack(pc0.x, pc0.y); cs[1] = f32x2_pack(pc0.z, pc0.w);
+                    cs[2] = f32x2_pack(pc1.x, pc1.y); cs[3] = f32x2_pack(pc1.z, pc1.w);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = 8 * i + rsub;
@@ -323,8 +375,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         const float4 x0 = ld_shared_f4(stg + r * 128 + (((2 * c8) ^ (r & 7)) << 4));
                         const float4 x1 = ld_shared_f4(stg + r * 128 + (((2 * c8 + 1) ^ (r & 7)) << 4));
                         if (row < M && col_ok) {
-                            uint64_t y[4] = {f32x2_add(f32x2_pack(x0.x, x0.y), bb[0]), f32x2_add(f32x2_pack(x0.z, x0.w), bb[1]),
-                                             f32x2_add(f32x2_pack(x1.x, x1.y), bb[2]), f32x2_add(f32x2_pack(x1.z, x1.w), bb[3])};
+                            uint64_t y[4] = {f32x2_pack(x0.x, x0.y), f32x2_pack(x0.z, x0.w), f32x2_pack(x1.x, x1.y),
+                                             f32x2_pack(x1.z, x1.w)};
+                            if (use_ln) {
+                                const uint64_t rs2 = f32x2_pack(ln_rs[i], ln_rs[i]), nm2 = f32x2_pack(ln_nm[i], ln_nm[i]);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) y[e] = f32x2_fma(y[e], rs2, f32x2_fma(cs[e], nm2, bb[e]));
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
+                            }
                             if (ep.act_gelu) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
@@ -347,6 +407,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     }
                 }
                 __syncwarp();   // staging tile is rewritten by the next chunk
+            }
+            if (ep.stat_out != nullptr && !ep.out_bf16 && row_base < M && n0 + half * EPI_COLS < N) {
+                // (sum, sum of squares) of this warp's 32 rows over its EPI_COLS columns: 8 lanes share a row
+                const int grp = (n0 + half * EPI_COLS) / EPI_COLS;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a1 = st1[i], a2 = st2[i];
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                    }
+                    const int row = row_base + 4 * i + (lane >> 3);
+                    if ((lane & 7) == 0 && row < M)
+                        ep.stat_out[static_cast<long long>(row) * ep.stat_groups + grp] = make_float2(a1, a2);
+                }
             }
         }
     }
@@ -468,12 +544,26 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
+
         CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAIR));
         attr_set = true;
     }
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
-    GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu};
+    if ((a.copy_bf16 || a.stat_out) && a.out_bf16)
+        return set_error(CVLM_ERR_ARG, "gemm: bf16 copy / row statistics need the fp32 output path");
+    if (a.copy_bf16 && ((reinterpret_cast<uintptr_t>(a.copy_bf16) & 7) || (a.ldc % 4)))
+        return set_error(CVLM_ERR_ARG, "gemm: bf16 copy must allow 8-byte vectors");
+    if (a.stat_out && a.stat_groups != (a.n + EPI_COLS - 1) / EPI_COLS)
+        return set_error(CVLM_ERR_ARG, "gemm: stat_groups must be ceil(n / %d)", EPI_COLS);
+    if (a.ln_rows && (!a.out_bf16 || !a.ln_colsum || (reinterpret_cast<uintptr_t>(a.ln_colsum) & 15) ||
+                      (reinterpret_cast<uintptr_t>(a.ln_rows) & 7)))
+        return set_error(CVLM_ERR_ARG, "gemm: the LayerNorm epilogue needs bf16 output, column sums and finalized row statistics");
+    if (a.copy_bf16 && (a.copy_bf16 == a.a1 || a.copy_bf16 == a.a2))
+        return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
+    GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
+               static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
+               reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum};
     const int tiles_n = (a.n + BN - 1) / BN;
     if (pair) {
         const int tiles_m = (a.m + 2 * BM - 1) / (2 * BM);

@@ -111,6 +111,36 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
         out[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
 }
+// (sum, sum of squares) partials per 128-column group -> (rstd, -mean * rstd) per row: the statistics half of
+// nn.LayerNorm (biased variance, eps inside the square root) for the GEMM epilogue that applies them.
+__global__ void ln_finalize_kernel(const float2* __restrict__ partial, int groups, float inv_k, float eps,
+                                   float2* __restrict__ out, long long rows) {
+    const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int g = 0; g < groups; ++g) {
+        const float2 p = __ldg(partial + row * groups + g);
+        s1 += p.x;
+        s2 += p.y;
+    }
+    const float mu = s1 * inv_k;
+    const float var = fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f);
+    const float rstd = rsqrtf(var + eps);
+    out[row] = make_float2(rstd, -mu * rstd);
+}
+
+int ln_finalize_launch(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
+                       cudaStream_t stream) {
+    if (!partial || !rows_out || groups <= 0 || width <= 0 || rows <= 0) return set_error(CVLM_ERR_ARG, "ln_finalize: bad argument");
+    const int threads = 256;
+    const long long blocks = (rows + threads - 1) / threads;
+    ln_finalize_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        reinterpret_cast<const float2*>(partial), groups, 1.0f / static_cast<float>(width), eps,
+        reinterpret_cast<float2*>(rows_out), rows);
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
 int cast_bf16_launch(const float* x, void* out, long long n, cudaStream_t stream) {
     if (!x || !out || n <= 0 || (n & 3)) return set_error(CVLM_ERR_ARG, "cast: bad arguments");
     const long long nvec = n >> 2;

@@ -21,10 +21,15 @@ def _ptr(t: Optional[torch.Tensor]):
 def gemm_bf16(a1: torch.Tensor, b1: torch.Tensor, a2: Optional[torch.Tensor] = None,
               b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out_dtype=torch.float32,
-              gelu: bool = False, n: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              gelu: bool = False, n: Optional[int] = None, out: Optional[torch.Tensor] = None,
+              copy_bf16: Optional[torch.Tensor] = None, stat_out: Optional[torch.Tensor] = None,
+              ln_rows: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[m, n] = epilogue(a1 @ b1.T (+ a2 @ b2.T)).  a*: bf16 [m, k*] (last dim contiguous, any row stride),
-    b*: bf16 [rows<=n, k*].  ``n`` defaults to b1.shape[0] rounded up to a multiple of 8."""
-    _need_cuda(a1, b1, a2, b2, bias, residual, out)
+    b*: bf16 [rows<=n, k*].  ``n`` defaults to b1.shape[0] rounded up to a multiple of 8.
+    LayerNorm fold (cvlm_op_gemm_bf16_ln): ``copy_bf16`` [m, n] bf16 and ``stat_out`` [m, ceil(n/128), 2] fp32 are
+    extra outputs of an fp32 GEMM; ``ln_rows`` [m, 2] (``ln_finalize`` of such statistics of the rows of a1) +
+    ``ln_colsum`` [n] make a bf16 GEMM compute rstd * (acc - mean * colsum) + bias."""
+    _need_cuda(a1, b1, a2, b2, bias, residual, out, copy_bf16, stat_out, ln_rows, ln_colsum)
     assert a1.dtype == torch.bfloat16 and b1.dtype == torch.bfloat16 and a1.stride(1) == 1 and b1.stride(1) == 1
     m, k1 = a1.shape
     b_rows = b1.shape[0]
@@ -37,12 +42,33 @@ def gemm_bf16(a1: torch.Tensor, b1: torch.Tensor, a2: Optional[torch.Tensor] = N
         assert a2.dtype == torch.bfloat16 and b2.dtype == torch.bfloat16 and a2.stride(1) == 1 and b2.stride(1) == 1
         k2 = a2.shape[1]
     lib = _lib.load()
-    _lib.check(lib.cvlm_op_gemm_bf16(
-        a1.data_ptr(), a1.stride(0), b1.data_ptr(), b1.stride(0), k1,
-        _ptr(a2), a2.stride(0) if a2 is not None else 0, _ptr(b2), b2.stride(0) if b2 is not None else 0, k2,
-        m, n, b_rows, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, res_row_mod,
-        out.data_ptr(), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0, 1 if gelu else 0,
-        _lib.stream_ptr()), "cvlm_op_gemm_bf16")
+    common = (a1.data_ptr(), a1.stride(0), b1.data_ptr(), b1.stride(0), k1,
+              _ptr(a2), a2.stride(0) if a2 is not None else 0, _ptr(b2), b2.stride(0) if b2 is not None else 0, k2,
+              m, n, b_rows, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, res_row_mod,
+              out.data_ptr(), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0, 1 if gelu else 0)
+    if copy_bf16 is None and stat_out is None and ln_rows is None:
+        _lib.check(lib.cvlm_op_gemm_bf16(*common, _lib.stream_ptr()), "cvlm_op_gemm_bf16")
+        return out
+    if copy_bf16 is not None:
+        assert copy_bf16.dtype == torch.bfloat16 and copy_bf16.stride(1) == 1
+    if stat_out is not None:
+        assert stat_out.dtype == torch.float32 and stat_out.is_contiguous() and stat_out.shape == (m, -(-n // _lib.STAT_GROUP_COLS), 2)
+    if ln_rows is not None:
+        assert ln_rows.dtype == torch.float32 and ln_rows.is_contiguous() and ln_rows.shape == (m, 2)
+        assert ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() >= n
+    _lib.check(lib.cvlm_op_gemm_bf16_ln(*common, _ptr(copy_bf16), copy_bf16.stride(0) if copy_bf16 is not None else 0,
+                                        _ptr(stat_out), _ptr(ln_rows), _ptr(ln_colsum), _lib.stream_ptr()),
+               "cvlm_op_gemm_bf16_ln")
+    return out
+
+
+def ln_finalize(stat: torch.Tensor, width: int, eps: float) -> torch.Tensor:
+    """[rows, groups, 2] partial (sum, sum of squares) -> [rows, 2] = (rstd, -mean * rstd)."""
+    _need_cuda(stat)
+    assert stat.dtype == torch.float32 and stat.is_contiguous() and stat.dim() == 3 and stat.shape[2] == 2
+    out = torch.empty(stat.shape[0], 2, device=stat.device, dtype=torch.float32)
+    _lib.check(_lib.load().cvlm_op_ln_finalize(stat.data_ptr(), stat.shape[1], width, eps, out.data_ptr(), stat.shape[0],
+                                               _lib.stream_ptr()), "cvlm_op_ln_finalize")
     return out
 
 

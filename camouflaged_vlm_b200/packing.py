@@ -10,6 +10,11 @@ All transformations are exact in real arithmetic:
     ``oracle/encoder_oracle.py::prompts``; our stem keeps ``x0 = patch + pos_embed`` only, so the
     pos_embed part of that linear map is precomputed here (``emb.cst``).
   * prompt_{i+1} = shared_mlp(G_{i+1}) is folded into block i's lin2 (bias ``lin2.bf = b2 + b_s``).
+  * norm1 (image_encoder.py:436) is folded around the GEMMs on either side of it:
+    ``LN(x) W^T + b = rstd * (x W'^T - mu * c) + (W beta + b)`` with ``W' = W_qkv * gamma`` (column scale) and
+    ``c[n] = sum_k W'[n, k]``.  ``c`` is summed over the ROUNDED operand the tensor cores see, so the
+    mean term cancels exactly what the GEMM accumulates for a constant row.  (norm2 stays a kernel: its
+    neighbours, proj and lin1, are the two GEMMs whose epilogues have no slack -- measured, DESIGN.md.)
 ``dtype=torch.float32`` yields the same tensors unrounded for the fp32 check path.
 """
 from typing import Dict
@@ -91,16 +96,18 @@ def pack_weights(sd: Dict[str, torch.Tensor], cfg: EncoderConfig, device, dtype=
     for i in range(depth):
         b, o = f"blocks.{i}.", f"blk.{i}."
         size = cfg.block_window(i) or cfg.grid      # Attention.input_size, image_encoder.py:422
-        out[o + "ln1.w"] = vec(g(b + "norm1.weight"))
-        out[o + "ln1.b"] = vec(g(b + "norm1.bias"))
-        out[o + "qkv.w"] = mat(g(b + "attn.qkv.weight"))
+        g1, be1 = g(b + "norm1.weight"), g(b + "norm1.bias")
+        w_qkv = g(b + "attn.qkv.weight")
+        out[o + "qkv.w"] = mat(w_qkv * g1[None, :])
+        out[o + "qkv.c"] = vec(out[o + "qkv.w"].double().sum(1))
         qb = torch.zeros(3 * D, device=device, dtype=f32)
         b_v = torch.zeros(D, device=device, dtype=f32)
         if cfg.qkv_bias:
             full = g(b + "attn.qkv.bias")
             qb[:D] = full[:D]
             b_v = full[2 * D:]
-        out[o + "qkv.b"] = qb
+        # W beta stays on K and V: it is present for real tokens only (the reference pads AFTER norm1)
+        out[o + "qkv.b"] = vec(qb.double() + w_qkv.double() @ be1.double())
         if cfg.use_rel_pos:
             out[o + "relh"] = mat(_resize_rel_pos(g(b + "attn.rel_pos_h"), size))
             out[o + "relw"] = mat(_resize_rel_pos(g(b + "attn.rel_pos_w"), size))

@@ -117,6 +117,26 @@ int cvlm_op_gemm_bf16(const void* a1, long long lda1, const void* b1, long long 
                       const float* bias, const float* residual, long long ldr, int res_row_mod, void* out,
                       long long ldo, int out_bf16, int act_gelu, cvlm_stream_t stream);
 
+/* Width of one column group of the row statistics below (one epilogue warp's share of an accumulator tile). */
+#define CVLM_STAT_GROUP_COLS 128
+
+/* The same GEMM with nn.LayerNorm folded around it (image_encoder.py:430-446 norm1 / norm2; DESIGN.md "LayerNorm fold").
+ * Producer options (fp32 output only): copy_bf16 != NULL also stores bf16(out) with row stride ldc (must not alias
+ * a1 / a2); stat_out != NULL receives fp32 [m, ceil(n/CVLM_STAT_GROUP_COLS), 2] = per row and column group (sum, sum of squares).
+ * Consumer options (bf16 output only): ln_rows != NULL is fp32 [m, 2] = (rstd, -mean*rstd) of this GEMM's A rows
+ * (cvlm_op_ln_finalize); the epilogue stores rstd * (acc - mean * ln_colsum[n]) + bias[n] (then GELU), i.e.
+ * LayerNorm(x) W^T + b when B holds gamma-scaled weights, ln_colsum their row sums and bias = W beta + b. */
+int cvlm_op_gemm_bf16_ln(const void* a1, long long lda1, const void* b1, long long ldb1, int k1, const void* a2,
+                         long long lda2, const void* b2, long long ldb2, int k2, int m, int n, int b_rows,
+                         const float* bias, const float* residual, long long ldr, int res_row_mod, void* out,
+                         long long ldo, int out_bf16, int act_gelu, void* copy_bf16, long long ldc, float* stat_out,
+                         const float* ln_rows, const float* ln_colsum, cvlm_stream_t stream);
+
+/* partial fp32 [rows, groups, 2] (stat_out above) -> rows_out fp32 [rows, 2] = (rstd, -mean*rstd) of a LayerNorm of
+ * `width` columns (biased variance, eps inside the square root). */
+int cvlm_op_ln_finalize(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
+                        cvlm_stream_t stream);
+
 /* Window (window>0) or global (window==0) attention with decomposed rel-pos on the token-major qkv
  * buffer bf16 [batch*g*g, 3*heads*head_dim] (K and V stored without bias); out bf16 [batch*g*g, D]. */
 int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,

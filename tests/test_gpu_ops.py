@@ -128,6 +128,39 @@ def test_gemm_two_k_segments_and_strided_operands(gemm_mode):
     assert torch.all(got[:, 10:] == 0)
 
 
+@pytest.mark.parametrize("m,d,n", [(512, 1280, 3840), (1000, 320, 960), (4096, 768, 3072)])
+def test_gemm_layernorm_fold(m, d, n, gemm_mode):
+    """nn.LayerNorm folded around two GEMMs: the producer (fp32 residual epilogue) leaves bf16(x) and per-row
+    partial (sum, sum of squares); the consumer normalises in its epilogue.  Reference: LN in fp32, then the GEMM."""
+    k0 = 256
+    a0 = _randn(m, k0, seed=60, dtype=torch.bfloat16)
+    w0 = _randn(d, k0, seed=61, dtype=torch.bfloat16, scale=0.08)
+    res = _randn(m, d, seed=62) * 2 + 0.7                     # a mean the fold has to subtract
+    x_want = a0.float() @ w0.float().t() + res
+    groups = -(-d // 128)                                     # CVLM_STAT_GROUP_COLS
+    xb = torch.empty(m, d, device=DEV, dtype=torch.bfloat16)
+    stat = torch.full((m, groups, 2), float("nan"), device=DEV)
+    x = ops.gemm_bf16(a0, w0, residual=res, copy_bf16=xb, stat_out=stat)
+    assert _rel(x, x_want) < 1e-5
+    assert torch.equal(xb, x.bfloat16())
+    assert _rel(stat[:, :, 0].sum(1), x.sum(1)) < 1e-5 and _rel(stat[:, :, 1].sum(1), (x * x).sum(1)) < 1e-5
+    gamma, beta = 1 + 0.1 * _randn(d, seed=63), 0.1 * _randn(d, seed=64)
+    w = _randn(n, d, seed=65, scale=0.05)
+    b = _randn(n, seed=66, scale=0.1)
+    ws = (w * gamma[None, :]).bfloat16()
+    colsum = ws.double().sum(1).float()
+    bias = (b.double() + w.double() @ beta.double()).float()
+    want = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-6) @ w.t() + b
+    rows = ops.ln_finalize(stat, d, 1e-6)
+    mu, var = x.double().mean(1), x.double().var(1, unbiased=False)
+    assert _rel(rows[:, 0], (var + 1e-6).rsqrt()) < 1e-5 and _rel(rows[:, 1], -mu * (var + 1e-6).rsqrt()) < 1e-4
+    got = ops.gemm_bf16(xb, ws, bias=bias, out_dtype=torch.bfloat16, ln_rows=rows, ln_colsum=colsum)
+    # bf16 x, bf16 gamma-scaled weights, bf16 output: three roundings of 2^-9
+    assert _rel(got.float(), want) < 6e-3
+    got_g = ops.gemm_bf16(xb, ws, bias=bias, out_dtype=torch.bfloat16, gelu=True, ln_rows=rows, ln_colsum=colsum)
+    assert _rel(got_g.float(), torch.nn.functional.gelu(want)) < 8e-3
+
+
 def test_gemm_rejects_bad_arguments():
     from camouflaged_vlm_b200._lib import CvlmError
     a = _randn(128, 64, dtype=torch.bfloat16)

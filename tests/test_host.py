@@ -42,7 +42,7 @@ def test_host_side_validation_without_gpu(lib):
     cc.rank, cc.rank_pad, cc.use_abs_pos = 40, 40, 1
     assert lib.cvlm_encoder_create(C.byref(cc), C.byref(h)) == 0
     per_image = lib.cvlm_encoder_workspace_bytes(h, 1)
-    assert 80e6 < per_image < 100e6                                       # ~85 MB / image
+    assert 85e6 < per_image < 105e6                                       # ~96 MB / image
     assert abs(lib.cvlm_encoder_workspace_bytes(h, 32) - 32 * per_image) < 1e5
     assert lib.cvlm_encoder_set_tensor(h, b"patch.w", None, 16) < 0       # null pointer rejected
     assert lib.cvlm_encoder_destroy(h) == 0
@@ -84,7 +84,15 @@ def test_packing_shapes_and_folds():
     assert p["lw.w"].shape == (cfg.depth * rp, rp) and p["lw.w"].dtype == torch.bfloat16
     assert p["emb.cst"].shape == (cfg.tokens, rp) and p["emb.cst"].dtype == torch.float32
     d = cfg.embed_dim
-    assert torch.all(p["blk.0.qkv.b"][d:] == 0)                           # K / V bias folded away
+    # K / V carry no Linear bias (folded away); what is left on them is W beta of the folded norm1
+    w, beta = sd["blocks.0.attn.qkv.weight"].double(), sd["blocks.0.norm1.bias"].double()
+    want_b = w @ beta
+    want_b[:d] += sd["blocks.0.attn.qkv.bias"][:d].double()
+    assert torch.allclose(p["blk.0.qkv.b"].double(), want_b, atol=1e-6)
+    # norm1 folded into qkv: gamma scales the weight columns, colsum is taken over the ROUNDED operand
+    gamma = sd["blocks.0.norm1.weight"]
+    assert torch.equal(p["blk.0.qkv.w"], (sd["blocks.0.attn.qkv.weight"] * gamma[None, :]).bfloat16())
+    assert torch.allclose(p["blk.0.qkv.c"].double(), p["blk.0.qkv.w"].double().sum(1), atol=1e-5)
     b_v = sd["blocks.0.attn.qkv.bias"][2 * d:]
     want = sd["blocks.0.attn.proj.bias"] + sd["blocks.0.attn.proj.weight"] @ b_v
     assert torch.allclose(p["blk.0.proj.b"], want, atol=1e-6)

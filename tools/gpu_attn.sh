@@ -1,6 +1,6 @@
 #!/bin/bash
 # Attention iteration visit: attention op tests, then op-level timings for the current kernels (per exp2
-# polynomial share) and the gen-1 kernels.
+# polynomial share) and the mma.sync fallback kernel.
 TAG=${1:-a}
 O=gpurun_out
 mkdir -p $O
@@ -14,5 +14,5 @@ for P in ${3:-0 2 4 6 8}; do
   CVLM_ATTN_POLY=$P timeout 600 python tools/op_bench.py ${2:-8} attn 2>&1 | tail -3 | tee -a $L
   if fault $L; then echo "fault, stopping" | tee -a $L; exit 3; fi
 done
-echo "=== op bench (gen1)" | tee -a $L
-CVLM_ATTN_GEN1=1 timeout 600 python tools/op_bench.py ${2:-8} attn 2>&1 | tail -3 | tee -a $L
+echo "=== op bench (mma.sync kernel)" | tee -a $L
+CVLM_ATTN_LEGACY=1 timeout 600 python tools/op_bench.py ${2:-8} attn 2>&1 | tail -3 | tee -a $L
