@@ -55,6 +55,12 @@ struct GemmArgs {
     float* stat_out = nullptr;  int stat_groups = 0;     // producer: fp32 [m, stat_groups, 2], stat_groups = ceil(n / CVLM_STAT_GROUP_COLS)
     const float* ln_rows = nullptr;                      // consumer: fp32 [m, 2] = (rstd, -mean * rstd) of the A rows
     const float* ln_colsum = nullptr;                    // consumer: fp32 [n]
+    // Batched mode: `batch` independent products that share A1 / A2.  Entry b multiplies by the B columns
+    // [b * b_k_off, b * b_k_off + k) and owns output / residual rows [b * batch_rows, b * batch_rows + m).
+    int batch = 1;
+    int b_k_off = 0;
+    long long batch_rows = 0;
+    int act_abs = 0;           // fp32 path: store |value|
 };
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
@@ -74,6 +80,10 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
 int ln_finalize_launch(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
                        cudaStream_t stream);
 int cast_bf16_launch(const float* x, void* out, long long n, cudaStream_t stream);
+// ---- high-pass filter of the adapter (highpass.cu)
+long long high_pass_scratch_bytes(int batch, int chans, int img_size);
+int high_pass_launch(const float* images, float* out, int batch, int chans, int img_size, const void* pcat,
+                     const void* npr, const void* pi, void* scratch, long long scratch_bytes, cudaStream_t stream);
 int im2col_patch_launch(const float* img, void* out, int batch, int chans, int img_size, int patch,
                         cudaStream_t stream);
 int im2col_3x3_launch(const void* x_nhwc_bf16, void* out, int batch, int grid_side, int chans, cudaStream_t stream);

@@ -65,7 +65,7 @@ static inline long long align_up(long long v, long long a) { return (v + a - 1) 
 struct Workspace {
     long long off_x, off_a, off_big, off_hand, off_t, off_gall, total;
     long long big_cols;
-    long long off_xb, off_stat, off_rows;
+    long long off_xb, off_stat, off_rows, off_hp, off_hps, hps_bytes;
 };
 
 static Workspace plan_workspace(const cvlm_encoder_config& c, int batch) {
@@ -90,6 +90,11 @@ static Workspace plan_workspace(const cvlm_encoder_config& c, int batch) {
     w.off_xb = off;    off = align_up(off + M * D * 2, 1024);              // bf16 copy of the residual stream
     w.off_stat = off;  off = align_up(off + M * ((D + CVLM_STAT_GROUP_COLS - 1) / CVLM_STAT_GROUP_COLS) * 8, 1024);   // (sum, sum sq)
     w.off_rows = off;  off = align_up(off + M * 8, 1024);                  // (rstd, -mean * rstd) per row
+    // high-pass filter: fp32 result + scratch (bf16 image copy and the half-transformed spectrum)
+    const long long img_elems = static_cast<long long>(batch) * c.in_chans * c.img_size * c.img_size;
+    w.off_hp = off;    off = align_up(off + img_elems * 4, 1024);
+    w.off_hps = off;   off = align_up(off + high_pass_scratch_bytes(batch, c.in_chans, c.img_size), 1024);
+    w.hps_bytes = high_pass_scratch_bytes(batch, c.in_chans, c.img_size);
     w.total = off;
     return w;
 }
@@ -144,7 +149,7 @@ struct Fwd {
 static int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
                         float* const* interm, int stop_after_block, float* x_out, void* workspace,
                         long long workspace_bytes, cudaStream_t stream) {
-    if (!enc || !images || !highpass || !workspace) return set_error(CVLM_ERR_ARG, "forward: null argument");
+    if (!enc || !images || !workspace) return set_error(CVLM_ERR_ARG, "forward: null argument");
     if (batch <= 0) return set_error(CVLM_ERR_ARG, "forward: batch must be positive");
     const cvlm_encoder_config& c = enc->cfg;
     const Workspace ws = plan_workspace(c, batch);
@@ -193,6 +198,21 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
     CVLM_TRY(f.get("shared.b", 4LL * D, &sh_b));
 
     // ------------------------------------------------------------------ stem
+    if (!highpass) {   // PromptGenerator.fft (:332-353) as two GEMMs with the low-pass projector (highpass.cu)
+        const void *pcat, *npr, *ppi;
+        const long long n = c.img_size;
+        const long long np = (n + 63) / 64 * 64;
+        CVLM_TRY(f.get("hp.pcat", 4LL * n * n, &pcat));
+        CVLM_TRY(f.get("hp.npr", 2LL * n * np, &npr));
+        CVLM_TRY(f.get("hp.pi", 2LL * n * np, &ppi));
+        float* hp = reinterpret_cast<float*>(wsb + ws.off_hp);
+        f.launches += 2;    // cast + G1 + G2: three launches, one counted by run()
+        CVLM_TRY(f.run(K_GEMM_OTHER, [&] {
+            return high_pass_launch(images, hp, batch, c.in_chans, c.img_size, pcat, npr, ppi, wsb + ws.off_hps, ws.hps_bytes,
+                                    stream);
+        }));
+        highpass = hp;
+    }
     __nv_bfloat16* patches = big;
     __nv_bfloat16* patches_hp = big + M * kp;
     CVLM_TRY(f.run(K_OTHER, [&] { return im2col_patch_launch(images, patches, batch, c.in_chans, c.img_size, c.patch_size, stream); }));
@@ -494,6 +514,17 @@ int cvlm_op_gemm_bf16_ln(const void* a1, long long lda1, const void* b1, long lo
 int cvlm_op_ln_finalize(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
                         cvlm_stream_t stream) {
     return ln_finalize_launch(partial, groups, width, eps, rows_out, rows, static_cast<cudaStream_t>(stream));
+}
+
+long long cvlm_op_high_pass_scratch_bytes(int batch, int chans, int img_size) {
+    if (batch <= 0 || chans <= 0 || img_size <= 0) return set_error(CVLM_ERR_ARG, "high_pass_scratch_bytes: bad argument");
+    return high_pass_scratch_bytes(batch, chans, img_size);
+}
+
+int cvlm_op_high_pass(const float* images, float* out, int batch, int chans, int img_size, const void* pcat,
+                      const void* npr, const void* pi, void* scratch, long long scratch_bytes, cvlm_stream_t stream) {
+    return high_pass_launch(images, out, batch, chans, img_size, pcat, npr, pi, scratch, scratch_bytes,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,

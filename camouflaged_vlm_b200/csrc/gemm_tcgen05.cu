@@ -56,6 +56,12 @@ struct GemmEpi {
     // ... and consumer side
     const float2* ln_rows;        // bf16 path: (rstd, -mean * rstd) of this GEMM's A rows (ln_finalize_kernel)
     const float* ln_colsum;       // [n] sum_k B[n, k]
+    // batched mode (GemmArgs::batch): tile list = batch x tiles; batch b reads B at K offset b * b_k_off and owns
+    // output / residual rows [b * batch_rows, b * batch_rows + M)
+    int tiles_per_batch;
+    long long batch_rows;
+    int b_k_off;
+    int act_abs;                  // fp32 path: store |value|
 };
 
 // Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
@@ -177,8 +183,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-                const int m0 = (tile / tiles_n) * TILE_M + cta_rank * BM;
-                const int n0 = (tile % tiles_n) * BN + (PAIR ? cta_rank * (BN / 2) : 0);
+                const int bidx = tile / ep.tiles_per_batch, tl = tile - bidx * ep.tiles_per_batch;
+                const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM;
+                const int n0 = (tl % tiles_n) * BN + (PAIR ? cta_rank * (BN / 2) : 0);
+                const int bk = bidx * ep.b_k_off;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const bool second = kb >= kblocks1;
@@ -188,11 +196,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (A_STAGE + B_BYTES));
                         const uint32_t lead_bar = full_bar(stage) & kPeerBitMask;
                         tma_load_2d_pair(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, lead_bar, kc, m0);
-                        tma_load_2d_pair(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, lead_bar, kc, n0);
+                        tma_load_2d_pair(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, lead_bar, kc + bk, n0);
                     } else {
                         mbar_arrive_expect_tx(full_bar(stage), A_STAGE + B_BYTES);
                         tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), kc, m0);
-                        tma_load_2d(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, full_bar(stage), kc, n0);
+                        tma_load_2d(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, full_bar(stage), kc + bk, n0);
                     }
                     if (++stage == NSTAGE) {
                         stage = 0;
@@ -253,8 +261,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         int iter = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
             const int acc = iter & 1;
-            const int m0 = (tile / tiles_n) * TILE_M + cta_rank * BM, n0 = (tile % tiles_n) * BN;
+            const int bidx = tile / ep.tiles_per_batch, tl = tile - bidx * ep.tiles_per_batch;
+            const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM, n0 = (tl % tiles_n) * BN;
             const int row_base = m0 + quad * 32;
+            const long long brow = bidx * ep.batch_rows;          // first output row of this batch entry
             // LayerNorm of the A rows, applied to the accumulator (GemmArgs::ln_stat): this lane's 4 rows of the
             // bf16 path.  out = rstd * (acc - mu * colsum) + bias  ==  LN(x) * W^T + b  with gamma folded into W.
             float ln_rs[4] = {1.f, 1.f, 1.f, 1.f}, ln_nm[4] = {0.f, 0.f, 0.f, 0.f};
@@ -303,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         const int row = row_base + 4 * i + (lane >> 3);
                         rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (row < M && col < N) {
-                            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : brow + row;
                             rr[i] = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                         }
                     }
@@ -344,7 +354,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                             if (use_res) {
                                 x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
                             }
-                            *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = x;
+                            if (ep.act_abs) {
+                                x.x = fabsf(x.x); x.y = fabsf(x.y); x.z = fabsf(x.z); x.w = fabsf(x.w);
+                            }
+                            *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (brow + row) * ep.ldo + col) = x;
                             if (ep.copy_bf16 != nullptr) {
                                 uint2 pk;
                                 pk.x = pack_bf16(x.x, x.y);
@@ -390,7 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
                             }
                             if (ep.residual) {
-                                const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : row;
+                                const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : brow + row;
                                 const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                                 const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col + 4);
                                 y[0] = f32x2_add(y[0], f32x2_pack(r0.x, r0.y)); y[1] = f32x2_add(y[1], f32x2_pack(r0.z, r0.w));
@@ -402,7 +415,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                             f32x2_unpack(y[1], lo, hi); pk.y = pack_bf16(lo, hi);
                             f32x2_unpack(y[2], lo, hi); pk.z = pack_bf16(lo, hi);
                             f32x2_unpack(y[3], lo, hi); pk.w = pack_bf16(lo, hi);
-                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<long long>(row) * ep.ldo + col) = pk;
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + (brow + row) * ep.ldo + col) = pk;
                         }
                     }
                 }
@@ -526,18 +539,26 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)))
         return set_error(CVLM_ERR_ARG, "gemm: epilogue pointers / strides must allow 16-byte vectors");
     const int brows = a.b_rows > 0 ? a.b_rows : a.n;
+    const int nbatch = a.batch > 0 ? a.batch : 1;
+    if (nbatch > 1 && (a.copy_bf16 || a.stat_out || a.ln_rows || a.res_row_mod > 0))
+        return set_error(CVLM_ERR_ARG, "gemm: batched mode supports bias / GELU / residual / abs epilogues only");
+    if (a.act_abs && a.out_bf16) return set_error(CVLM_ERR_ARG, "gemm: abs needs the fp32 output path");
     // 256 x 256 cluster tiles whenever they fill the machine; CVLM_GEMM_MODE=1cta / pair forces one kernel
     // (read per call: the parity tests flip it to cover both kernels on every shape).
     const char* mode = getenv("CVLM_GEMM_MODE");
-    const int pair_tiles = ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
+    const int pair_tiles = nbatch * ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
     const bool pair = mode && mode[0] == 'p' ? true : mode && mode[0] == '1' ? false : pair_tiles >= num_sms() / 2;
     const int b_box = pair ? BN / 2 : BN;
     CUtensorMap tA1, tB1, tA2, tB2;
     CVLM_TRY(make_tensor_map(&tA1, a.a1, a.m, a.k1, a.lda1, BM));
-    CVLM_TRY(make_tensor_map(&tB1, a.b1, brows, a.k1, a.ldb1, b_box));
+    // batched mode: batch b reads B columns [b * b_k_off, b * b_k_off + k); with b_k_off == k the map ends exactly
+    // where the last batch entry does, so ragged K edges still zero-fill
+    if (nbatch > 1 && (a.b_k_off != a.k1 || (a.k2 > 0 && a.k2 != a.k1) || a.k1 % BK))
+        return set_error(CVLM_ERR_ARG, "gemm: batched mode needs b_k_off == k1 (== k2), a multiple of %d", BK);
+    CVLM_TRY(make_tensor_map(&tB1, a.b1, brows, static_cast<long long>(a.k1) * nbatch, a.ldb1, b_box));
     if (a.k2 > 0) {
         CVLM_TRY(make_tensor_map(&tA2, a.a2, a.m, a.k2, a.lda2, BM));
-        CVLM_TRY(make_tensor_map(&tB2, a.b2, brows, a.k2, a.ldb2, b_box));
+        CVLM_TRY(make_tensor_map(&tB2, a.b2, brows, static_cast<long long>(a.k2) * nbatch, a.ldb2, b_box));
     } else {
         tA2 = tA1;
         tB2 = tB1;
@@ -563,11 +584,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
                static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
-               reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum};
+               reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
+               a.act_abs};
     const int tiles_n = (a.n + BN - 1) / BN;
     if (pair) {
         const int tiles_m = (a.m + 2 * BM - 1) / (2 * BM);
-        const int clusters = tiles_m * tiles_n < num_sms() / 2 ? tiles_m * tiles_n : num_sms() / 2;
+        ep.tiles_per_batch = tiles_m * tiles_n;
+        const int total_tiles = nbatch * tiles_m * tiles_n;
+        const int clusters = total_tiles < num_sms() / 2 ? total_tiles : num_sms() / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
         cfg.blockDim = dim3(GEMM_THREADS);
@@ -580,13 +604,15 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CVLM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<true>, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, tiles_m,
-                                     tiles_n, ep));
+        CVLM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<true>, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n,
+                                     nbatch * tiles_m, tiles_n, ep));
     } else {
         const int tiles_m = (a.m + BM - 1) / BM;
-        const int grid = tiles_m * tiles_n < num_sms() ? tiles_m * tiles_n : num_sms();
+        ep.tiles_per_batch = tiles_m * tiles_n;
+        const int total_tiles = nbatch * tiles_m * tiles_n;
+        const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
         gemm_bf16_tcgen05_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n,
-                                                                             tiles_m, tiles_n, ep);
+                                                                             nbatch * tiles_m, tiles_n, ep);
     }
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;

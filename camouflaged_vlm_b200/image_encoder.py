@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .check_path import encoder_forward_check, high_pass
+from .check_path import encoder_forward_check
 from .common import LayerNorm2d, MLPBlock
 from .config import EncoderConfig
 from .packing import pack_weights, rank_pad
@@ -279,13 +279,13 @@ class ImageEncoderViT(nn.Module):
             for s in range(0, B, self.max_chunk):
                 e = min(B, s + self.max_chunk)
                 xc = x[s:e]
-                hp = high_pass(xc, cfg.freq_nums).contiguous()
                 ws = self._get_workspace(e - s, x.device)
                 iptr = None
                 if interm:
                     arr = (C.c_void_p * n_glob)(*[t[s:e].data_ptr() for t in interms])
                     iptr = C.cast(arr, C.POINTER(C.c_void_p))
-                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), hp.data_ptr(), e - s,
+                # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu)
+                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s,
                                                     out[s:e].data_ptr(), iptr, ws.data_ptr(), ws.numel(), stream),
                            "cvlm_encoder_forward")
                 launches += lib.cvlm_encoder_last_launch_count(self._handle)
@@ -302,10 +302,9 @@ class ImageEncoderViT(nn.Module):
         self._ensure_ready(x.device)
         lib = _lib.load()
         B = x.shape[0]
-        hp = high_pass(x, cfg.freq_nums).contiguous()
         ws = self._get_workspace(B, x.device)
         xo = torch.empty(B * cfg.tokens, cfg.embed_dim, device=x.device, dtype=torch.float32)
-        _lib.check(lib.cvlm_encoder_forward_partial(self._handle, x.data_ptr(), hp.data_ptr(), B, stop_after_block,
+        _lib.check(lib.cvlm_encoder_forward_partial(self._handle, x.data_ptr(), None, B, stop_after_block,
                                                     xo.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
                    "cvlm_encoder_forward_partial")
         return xo

@@ -134,6 +134,24 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def high_pass(images: torch.Tensor, pcat: torch.Tensor, npr: torch.Tensor, pi: torch.Tensor) -> torch.Tensor:
+    """PromptGenerator.fft as two GEMMs with the low-pass projector (packing.high_pass_matrices)."""
+    _need_cuda(images, pcat, npr, pi)
+    assert images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4
+    b, c, h, w = images.shape
+    hp_ = (h + 63) // 64 * 64
+    assert h == w and pcat.shape == (2 * h, h) and npr.shape == (h, hp_) and pi.shape == (h, hp_)
+    lib = _lib.load()
+    need = lib.cvlm_op_high_pass_scratch_bytes(b, c, h)
+    _lib.check(need, "cvlm_op_high_pass_scratch_bytes")
+    scratch = torch.empty(need, dtype=torch.uint8, device=images.device)
+    out = torch.empty_like(images)
+    _lib.check(lib.cvlm_op_high_pass(images.data_ptr(), out.data_ptr(), b, c, h, pcat.contiguous().data_ptr(),
+                                     npr.contiguous().data_ptr(), pi.contiguous().data_ptr(), scratch.data_ptr(), need,
+                                     _lib.stream_ptr()), "cvlm_op_high_pass")
+    return out
+
+
 def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> torch.Tensor:
     _need_cuda(x0, hand, w_t, cst)
     out = torch.empty(batch * tokens, rank_pad, device=x0.device, dtype=torch.bfloat16)

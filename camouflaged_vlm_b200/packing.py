@@ -38,6 +38,24 @@ def _resize_rel_pos(rel_pos: torch.Tensor, size: int) -> torch.Tensor:
     return rp.reshape(-1, want).permute(1, 0)
 
 
+def high_pass_matrices(n: int, rate: float, device, dtype=torch.bfloat16):
+    """The low-pass projector of PromptGenerator.fft (image_encoder.py:332-353) for an n x n image:
+    P[a, b] = (1/n) sum_{u in [-line, line)} exp(2 pi i u (a - b) / n),  line = int(sqrt(n*n*rate) // 2),
+    so that  fft(x, rate) = |x - Re(P x P^T)| = |x - Pr x Pr^T + Pi x Pi^T|.
+    Returns (pcat = [Pr; Pi] [2n, n], npr = -Pr, pi = Pi, the last two with their columns zero-padded to a
+    multiple of 64: csrc/highpass.cu contracts them against a per-image padded block)."""
+    line = int((n * n * rate) ** 0.5 // 2)
+    u = torch.arange(-line, line, dtype=torch.float64)
+    d = torch.arange(n, dtype=torch.float64)
+    ang = 2.0 * torch.pi * u[:, None] * d[None, :] / n                 # [2*line, n]: first column of the circulant
+    col_r, col_i = torch.cos(ang).sum(0) / n, torch.sin(ang).sum(0) / n
+    idx = (torch.arange(n)[:, None] - torch.arange(n)[None, :]) % n    # P[a, b] = col[(a - b) mod n]
+    pr, pi = col_r[idx], col_i[idx]
+    to = lambda t: t.to(device=device, dtype=dtype).contiguous()
+    pad = (n + 63) // 64 * 64 - n
+    return to(torch.cat([pr, pi], 0)), to(F.pad(-pr, (0, pad))), to(F.pad(pi, (0, pad)))
+
+
 @torch.no_grad()
 def pack_weights(sd: Dict[str, torch.Tensor], cfg: EncoderConfig, device, dtype=torch.bfloat16
                  ) -> Dict[str, torch.Tensor]:
@@ -125,6 +143,8 @@ def pack_weights(sd: Dict[str, torch.Tensor], cfg: EncoderConfig, device, dtype=
         b2 = g(b + "mlp.lin2.bias")
         out[o + "lin2.b"] = vec(b2)
         out[o + "lin2.bf"] = vec(b2 + b_s)
+
+    out["hp.pcat"], out["hp.npr"], out["hp.pi"] = high_pass_matrices(cfg.img_size, cfg.freq_nums, device, dtype)
 
     oc = cfg.out_chans
     out["neck.conv1.w"] = mat(g("neck.0.weight").reshape(oc, D))

@@ -75,7 +75,8 @@ long long cvlm_encoder_workspace_bytes(const cvlm_encoder* enc, int batch);
 
 /* ImageEncoderViT.forward(x, interm) (image_encoder.py:132-155).
  *   images     fp32 NCHW [batch, in_chans, img, img], device
- *   highpass   fp32 NCHW, same shape: PromptGenerator.fft(images, 0.25) (:332-353), device
+ *   highpass   NULL (computed here: hp.* tensors, csrc/highpass.cu), or fp32 NCHW of the same shape holding
+ *              PromptGenerator.fft(images, 0.25) (:332-353), device
  *   out        fp32 NCHW [batch, out_chans, g, g], device
  *   interm     NULL, or one device pointer per global block (in block order), each fp32 NHWC
  *              [batch, g, g, D]: receives the residual stream after that block; the Python module
@@ -157,6 +158,14 @@ int cvlm_op_im2col_patch16(const float* img, void* out, int batch, int chans, in
 int cvlm_op_im2col_3x3(const void* x_nhwc, void* out, int batch, int grid_side, int chans, cvlm_stream_t stream);
 
 int cvlm_op_cast_bf16(const float* x, void* out, long long n, cvlm_stream_t stream);
+
+/* PromptGenerator.fft(images, rate) (image_encoder.py:332-353) as two tcgen05 GEMMs with the low-pass projector
+ * (csrc/highpass.cu): out = |images - Pr X Pr^T + Pi X Pi^T| per channel image, fp32 [batch, chans, img, img].
+ * pcat = [Pr; Pi] bf16 [2*img, img]; npr = -Pr, pi = Pi bf16 [img, ceil(img/64)*64], zero padded (packing.py: hp.*);
+ * scratch: device bytes >= cvlm_op_high_pass_scratch_bytes. */
+long long cvlm_op_high_pass_scratch_bytes(int batch, int chans, int img_size);
+int cvlm_op_high_pass(const float* images, float* out, int batch, int chans, int img_size, const void* pcat,
+                      const void* npr, const void* pi, void* scratch, long long scratch_bytes, cvlm_stream_t stream);
 
 /* t = bf16(hand + cst + W_eg * scramble(x0)); see rowops.cu / DESIGN.md "adapter". */
 int cvlm_op_adapter_embed(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,

@@ -61,3 +61,19 @@ def test_check_path_global_only_and_window_larger_than_grid():
 def test_high_pass_matches_oracle():
     x = seeded_images(PRESETS["tiny"], 2, 7)
     assert orc.rel_l2(high_pass(x, 0.25), orc.high_pass(x, 0.25)) < 1e-6
+
+
+def test_high_pass_projector_matrices_reproduce_the_fft():
+    """csrc/highpass.cu replaces the FFT by  |x - Pr x Pr^T + Pi x Pi^T|  (packing.high_pass_matrices): exact in
+    fp64 for sizes with and without 64-alignment, including the asymmetric -line frequency (Pi != 0)."""
+    from camouflaged_vlm_b200.packing import high_pass_matrices
+    for n in (64, 160, 288):
+        x = torch.randn(1, 2, n, n, dtype=torch.float64, generator=torch.Generator().manual_seed(n))
+        pcat, npr, pi = high_pass_matrices(n, 0.25, "cpu", torch.float64)
+        npad = (n + 63) // 64 * 64
+        assert pcat.shape == (2 * n, n) and npr.shape == (n, npad) and pi.shape == (n, npad)
+        assert torch.all(npr[:, n:] == 0) and torch.all(pi[:, n:] == 0) and pi.abs().max() > 0
+        pr, pim = pcat[:n], pcat[n:]
+        assert torch.equal(npr[:, :n], -pr) and torch.equal(pi[:, :n], pim)
+        got = (x - pr @ x @ pr.t() + pim @ x @ pim.t()).abs()
+        assert orc.rel_l2(got.float(), orc.high_pass(x.float(), 0.25)) < 1e-6

@@ -214,3 +214,18 @@ def test_attention_wide_logit_range(window, qscale):
     got = ops.attention(qkv, relh, relw, batch, grid, window, heads, hd).float()
     assert torch.isfinite(got).all()
     assert _rel(got, want) < 8e-3
+
+
+@pytest.mark.parametrize("batch,n", [(2, 160), (1, 256), (2, 288), (2, 1024)])
+def test_high_pass_native(batch, n):
+    """PromptGenerator.fft as two tcgen05 GEMMs with the bf16 low-pass projector vs the fp32 FFT route.
+    Two bf16 contractions of length n: ~2e-3 relative (the result is rounded to bf16 by the next kernel anyway)."""
+    from camouflaged_vlm_b200.packing import high_pass_matrices
+    x = _randn(batch, 3, n, n, seed=70)
+    pcat, npr, pi = high_pass_matrices(n, 0.25, DEV)
+    got = ops.high_pass(x, pcat, npr, pi)
+    want = cp.high_pass(x, 0.25)
+    assert got.shape == want.shape and torch.all(got >= 0)
+    assert _rel(got, want) < 5e-3
+    # images are independent: a batch of one gives the same bits
+    assert torch.equal(ops.high_pass(x[:1].contiguous(), pcat, npr, pi), got[:1])
