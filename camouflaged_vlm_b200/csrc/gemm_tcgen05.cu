@@ -86,24 +86,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // (profiles/ncu_gemm_r1e: 55 % issue-active with two epilogue warps per scheduler).  The polynomial carries the
 // minus sign of "- |x| * E".
 __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
-    float x0, x1;
-    f32x2_unpack(x2, x0, x1);
-    const uint64_t ax2 = f32x2_pack(fabsf(x0), fabsf(x1));
+    // the scalar MUFU / max ops live inside asm blocks that unpack and re-pack the pair themselves: ptxas then
+    // allocates their results straight into the halves of the 64-bit register (no MOVs between the packed ops)
+    const uint64_t ax2 = f32x2_abs(x2);
     const uint64_t zs2 = f32x2_mul(ax2, f32x2_pack(0.8493218002880191f, 0.8493218002880191f));
-    float a0, a1, z0, z1;
-    f32x2_unpack(f32x2_fma(zs2, f32x2_pack(0.2727374808792225f, 0.2727374808792225f), f32x2_pack(1.0f, 1.0f)), a0, a1);
-    f32x2_unpack(f32x2_mul(zs2, zs2), z0, z1);
-    float t0, t1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(a0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(a1));
-    const float e0 = ex2_approx(-z0), e1 = ex2_approx(-z1);
-    const uint64_t t2 = f32x2_pack(t0, t1);
+    const uint64_t t2 = f32x2_rcp(f32x2_fma(zs2, f32x2_pack(0.2727374808792225f, 0.2727374808792225f), f32x2_pack(1.0f, 1.0f)));
+    const uint64_t e2 = f32x2_ex2_neg(f32x2_mul(zs2, zs2));
     uint64_t p = f32x2_fma(t2, f32x2_pack(-0.5307027145f, -0.5307027145f), f32x2_pack(0.7265760135f, 0.7265760135f));
     p = f32x2_fma(p, t2, f32x2_pack(-0.7107068705f, -0.7107068705f));
     p = f32x2_fma(p, t2, f32x2_pack(0.142248368f, 0.142248368f));
     p = f32x2_fma(p, t2, f32x2_pack(-0.127414796f, -0.127414796f));
-    p = f32x2_mul(f32x2_mul(p, t2), f32x2_pack(e0, e1));
-    return f32x2_fma(ax2, p, f32x2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+    p = f32x2_mul(f32x2_mul(p, t2), e2);
+    return f32x2_fma(ax2, p, f32x2_relu(x2));
 }
 
 // PAIR = false: one CTA per 128 x 256 tile (small problems).

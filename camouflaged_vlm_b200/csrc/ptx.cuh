@@ -312,6 +312,36 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// Scalar ops on both halves of a pair, unpacked and re-packed inside one asm block so that no MOV is needed
+__device__ __forceinline__ uint64_t f32x2_abs(uint64_t x) {
+    uint64_t r;
+    asm("and.b64 %0, %1, 0x7fffffff7fffffff;" : "=l"(r) : "l"(x));
+    return r;
+}
+__device__ __forceinline__ uint64_t f32x2_rcp(uint64_t x) {
+    uint64_t r;
+    asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %1;\n\trcp.approx.ftz.f32 a, a;\n\trcp.approx.ftz.f32 b, b;\n\t"
+        "mov.b64 %0, {a, b};\n\t}"
+        : "=l"(r)
+        : "l"(x));
+    return r;
+}
+__device__ __forceinline__ uint64_t f32x2_ex2_neg(uint64_t x) {      // (2^-lo, 2^-hi)
+    uint64_t r;
+    asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %1;\n\tneg.f32 a, a;\n\tneg.f32 b, b;\n\tex2.approx.ftz.f32 a, a;\n\t"
+        "ex2.approx.ftz.f32 b, b;\n\tmov.b64 %0, {a, b};\n\t}"
+        : "=l"(r)
+        : "l"(x));
+    return r;
+}
+__device__ __forceinline__ uint64_t f32x2_relu(uint64_t x) {
+    uint64_t r;
+    asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %1;\n\tmax.f32 a, a, 0f00000000;\n\tmax.f32 b, b, 0f00000000;\n\t"
+        "mov.b64 %0, {a, b};\n\t}"
+        : "=l"(r)
+        : "l"(x));
+    return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
