@@ -304,17 +304,19 @@ def run_ours(args):
     if not args.skip_e2e:
         x_host = torch.empty(B, cfg.in_chans, cfg.img_size, cfg.img_size, pin_memory=True)
         x_host.copy_(x_dev)
-        out_host = torch.empty(B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
-        x_in = torch.empty_like(x_dev)
-        gathered = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev) if world > 1 else None
+        out_host = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
+
+        def gather(emb):                                        # embeddings gathered over NVLink (configs[2])
+            if world == 1:
+                return emb
+            full = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev)
+            dist.all_gather_into_tensor(full, emb)
+            return full
 
         def e2e_step():
-            x_in.copy_(x_host, non_blocking=True)
-            out = step(x_in)
-            emb = out[0] if interm else out
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, emb)      # embeddings gathered over NVLink (configs[2])
-            out_host.copy_(emb, non_blocking=True)
+            # the public host-buffer call: chunked H2D on a copy stream under the encoder, (all-gather,) D2H
+            with torch.no_grad():
+                model.forward_host(x_host, out_host=out_host, chunk=8, gather=gather if world > 1 else None, interm=interm)
 
         e2e_step()
         barrier()
@@ -327,9 +329,11 @@ def run_ours(args):
         e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * out_host.numel() * 4,
                "ms_per_step": ms_e2e / K,
-               "note": "pinned host -> device copy, forward(x, interm), "
+               "note": "ImageEncoderViT.forward_host: pinned host -> device in chunks of 8 on a copy stream under "
+                       "forward(x, interm) of the previous chunk, "
                        + ("NCCL all_gather_into_tensor of the embeddings, " if world > 1 else "")
-                       + "device -> pinned host copy of the [B,256,64,64] embedding; whole-job bytes"}
+                       + "device -> pinned host copy of the embeddings; whole-job bytes (every rank copies the "
+                         "gathered embeddings out)"}
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None

@@ -196,6 +196,8 @@ class ImageEncoderViT(nn.Module):
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
         self._workspace: Optional[torch.Tensor] = None
+        self._stage = None             # forward_host: two device staging buffers + a copy stream
+        self._copy_stream = None
         self.last_launch_count = 0
 
     # ------------------------------------------------------------------ packed-weight cache
@@ -231,7 +233,7 @@ class ImageEncoderViT(nn.Module):
                                                        t.numel() * t.element_size()), f"set_tensor({name})")
             self._packed_key = key
 
-    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspace")
+    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspace", "_stage", "_copy_stream")
 
     def __getstate__(self):
         # copy.deepcopy / pickle must not share the native handle or the device caches
@@ -268,31 +270,99 @@ class ImageEncoderViT(nn.Module):
             raise ValueError(f"expected input [B, {cfg.in_chans}, {cfg.img_size}, {cfg.img_size}], got {tuple(x.shape)}")
         with torch.no_grad():
             x = x.detach().to(torch.float32).contiguous()
-            self._ensure_ready(x.device)
-            lib = _lib.load()
             B, g, D = x.shape[0], cfg.grid, cfg.embed_dim
             out = torch.empty(B, cfg.out_chans, g, g, device=x.device, dtype=torch.float32)
             n_glob = sum(1 for i in range(cfg.depth) if cfg.block_window(i) == 0)
             interms = [torch.empty(B, g, g, D, device=x.device, dtype=torch.float32) for _ in range(n_glob)] if interm else []
-            stream = _lib.stream_ptr()
-            launches = 0
-            for s in range(0, B, self.max_chunk):
-                e = min(B, s + self.max_chunk)
-                xc = x[s:e]
-                ws = self._get_workspace(e - s, x.device)
-                iptr = None
-                if interm:
-                    arr = (C.c_void_p * n_glob)(*[t[s:e].data_ptr() for t in interms])
-                    iptr = C.cast(arr, C.POINTER(C.c_void_p))
-                # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu)
-                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s,
-                                                    out[s:e].data_ptr(), iptr, ws.data_ptr(), ws.numel(), stream),
-                           "cvlm_encoder_forward")
-                launches += lib.cvlm_encoder_last_launch_count(self._handle)
-            self.last_launch_count = launches
+            self._run(x, out, interms)
         if interm:
             return out, [t.permute(0, 3, 1, 2) for t in interms]     # views, like image_encoder.py:148
         return out
+
+    def _run(self, x: torch.Tensor, out: torch.Tensor, interms: List[torch.Tensor]) -> None:
+        """One or more C-ABI calls (chunks of ``max_chunk`` images) writing into caller-provided device tensors:
+        ``out`` [B,out,g,g] and, when not empty, ``interms`` (one [B,g,g,D] NHWC tensor per global block)."""
+        self._ensure_ready(x.device)
+        lib = _lib.load()
+        B = x.shape[0]
+        stream = _lib.stream_ptr()
+        launches = 0
+        for s in range(0, B, self.max_chunk):
+            e = min(B, s + self.max_chunk)
+            xc = x[s:e]
+            ws = self._get_workspace(e - s, x.device)
+            iptr = None
+            if interms:
+                arr = (C.c_void_p * len(interms))(*[t[s:e].data_ptr() for t in interms])
+                iptr = C.cast(arr, C.POINTER(C.c_void_p))
+            # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu)
+            _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s, out[s:e].data_ptr(), iptr,
+                                                ws.data_ptr(), ws.numel(), stream), "cvlm_encoder_forward")
+            launches += lib.cvlm_encoder_last_launch_count(self._handle)
+        self.last_launch_count = launches
+
+    @torch.no_grad()
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunk: int = 8,
+                     gather: Optional[Any] = None, interm: bool = False):
+        """Embeddings for a batch that lives in HOST memory (``x_host`` fp32 [B,3,S,S], ideally pinned): the batch is
+        cut into chunks of ``chunk`` images and the host->device copy of chunk i+1 and the device->host copy of the
+        embeddings of chunk i-1 run on a copy stream underneath the encoder of chunk i (two device staging buffers).
+        ``gather`` (optional) maps the device embeddings of the whole batch to what should be copied out, e.g.
+        ``dist.gather_embeddings``.  Returns ``out_host`` ([B,out,g,g] fp32, pinned if allocated here), valid once the
+        current stream has been synchronised; with ``interm=True`` also the list of per-global-block embeddings, which
+        stay on the device (NCHW views, like ``forward``)."""
+        cfg = self._cfg
+        if x_host.is_cuda:
+            raise ValueError("forward_host takes a host tensor; call the module directly for device tensors")
+        B, g = x_host.shape[0], cfg.grid
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        emb = torch.empty(B, cfg.out_chans, g, g, device=dev, dtype=torch.float32)
+        n_glob = sum(1 for i in range(cfg.depth) if cfg.block_window(i) == 0)
+        interms = [torch.empty(B, g, g, cfg.embed_dim, device=dev, dtype=torch.float32) for _ in range(n_glob)] if interm else []
+        shape = (min(chunk, B),) + tuple(x_host.shape[1:])
+        if getattr(self, "_stage", None) is None or self._stage[0].shape != shape or self._stage[0].device != dev:
+            self._stage = [torch.empty(shape, device=dev, dtype=torch.float32) for _ in range(2)]
+        stage = self._stage
+        ready = [torch.cuda.Event() for _ in range(2)]        # staging buffer filled
+        free = [torch.cuda.Event() for _ in range(2)]         # staging buffer consumed by the encoder
+        spans = [(s, min(B, s + chunk)) for s in range(0, B, chunk)]
+        cs.wait_stream(main)
+
+        def upload(i):
+            s, e = spans[i]
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(free[i % 2])
+                stage[i % 2][:e - s].copy_(x_host[s:e], non_blocking=True)
+                ready[i % 2].record(cs)
+
+        if gather is None and out_host is None:
+            out_host = torch.empty(B, cfg.out_chans, g, g, dtype=torch.float32, pin_memory=True)
+        upload(0)
+        for i, (s, e) in enumerate(spans):
+            if i + 1 < len(spans):
+                upload(i + 1)
+            main.wait_event(ready[i % 2])
+            self._run(stage[i % 2][:e - s], emb[s:e], [t[s:e] for t in interms])
+            free[i % 2].record(main)
+            if gather is None:                      # this chunk's embeddings go out under the next chunk's encoder
+                with torch.cuda.stream(cs):
+                    cs.wait_event(free[i % 2])
+                    out_host[s:e].copy_(emb[s:e], non_blocking=True)
+        if gather is None:
+            main.wait_stream(cs)
+        else:
+            result = gather(emb)
+            if out_host is None:
+                out_host = torch.empty(tuple(result.shape), dtype=torch.float32, pin_memory=True)
+            out_host.copy_(result, non_blocking=True)
+        if interm:
+            return out_host, [t.permute(0, 3, 1, 2) for t in interms]
+        return out_host
 
     @torch.no_grad()
     def forward_partial(self, x: torch.Tensor, stop_after_block: int) -> torch.Tensor:

@@ -132,3 +132,30 @@ def test_forward_refuses_cpu_and_grad():
         m(seeded_images(cfg, 1))                                       # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         m(seeded_images(cfg, 1).cuda())                                # grad mode: forward-only
+
+
+def test_encoder_vit_b_full_geometry_against_oracle():
+    """ViT-B at 1024^2 (BASELINE.json config 5): head_dim 64 through the tcgen05 attention kernels (64x64 global
+    grid, 14x14 windows), CTA-pair GEMMs, norm1 fold and the native high-pass, against the oracle on the host."""
+    cfg = PRESETS["vit_b"]
+    sd = seeded_state_dict(cfg, 4)
+    m = _encoder(cfg, 4)
+    x = seeded_images(cfg, 1, 4)
+    with torch.no_grad():
+        out, interm = m(x.cuda(), interm=True)
+    want, want_i = orc.encoder_forward(sd, cfg, x, interm=True)
+    assert orc.rel_l2(out.cpu(), want) < BF16_TOL
+    for a, b in zip(interm, want_i):
+        assert orc.rel_l2(a.cpu(), b) < BF16_TOL
+
+
+def test_forward_host_pipelines_chunks_and_matches_forward():
+    """forward_host: chunked, copy-stream-overlapped host path == one device forward, bit for bit."""
+    cfg = PRESETS["tiny"]
+    m = _encoder(cfg)
+    x = seeded_images(cfg, 5)
+    with torch.no_grad():
+        want = m(x.cuda())
+        got = m.forward_host(x.pin_memory(), chunk=2)
+    torch.cuda.synchronize()
+    assert got.is_pinned() and torch.equal(got, want.cpu())

@@ -18,25 +18,25 @@ echo "bench exit $?" | tee -a $O/round_$TAG.log
 tail -c 3000 $O/bench_$TAG.json | tee -a $O/round_$TAG.log
 tail -5 $O/bench_$TAG.err | tee -a $O/round_$TAG.log
 if [ "$2" == "noncu" ]; then exit 0; fi
-KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|attn_global_tc_kernel|attn_window_tc_kernel|layernorm_kernel|im2col|cast_bf16_kernel|adapter_embed_kernel|layernorm_nchw_kernel'
+KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|attn_global_tc2_kernel|attn_window_tc2_kernel|layernorm_kernel|ln_finalize_kernel|im2col|cast_bf16_kernel|cast_pad_rows_kernel|adapter_embed_kernel|layernorm_nchw_kernel'
 BENCH="python bench.py --steps 1 --warmup 3 --batch 32 --skip-cpu-baseline --skip-e2e"
 echo "=== ncu launch list" | tee -a $O/round_$TAG.log
 $BENCH > $O/plain_$TAG.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 720 -c 240 --csv \
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 729 -c 243 --csv \
     --log-file $O/launches_$TAG.csv $BENCH > $O/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?" | tee -a $O/round_$TAG.log
 echo "=== ncu full (gemm: qkv / proj / lin1 / lin2 of one block)" | tee -a $O/round_$TAG.log
 $BENCH > $O/plain2_$TAG.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05_kernel -s 448 -c 4 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05_kernel -s 461 -c 4 \
     -o $O/prof_gemm_$TAG -f $BENCH > $O/ncu_full_$TAG.log 2>&1
 echo "ncu full gemm exit $?" | tee -a $O/round_$TAG.log
 echo "=== ncu full (attention)" | tee -a $O/round_$TAG.log
 $BENCH > $O/plain3_$TAG.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:attn_global_tc_kernel -s 13 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:attn_global_tc2_kernel -s 13 -c 1 \
     -o $O/prof_attn_global_$TAG -f $BENCH > $O/ncu_full_ag_$TAG.log 2>&1
 echo "ncu full attn global exit $?" | tee -a $O/round_$TAG.log
 $BENCH > $O/plain4_$TAG.log 2>&1 && \
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:attn_window_tc_kernel -s 90 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:attn_window_tc2_kernel -s 90 -c 1 \
     -o $O/prof_attn_window_$TAG -f $BENCH > $O/ncu_full_aw_$TAG.log 2>&1
 echo "ncu full attn window exit $?" | tee -a $O/round_$TAG.log
 tail -3 $O/ncu_full_aw_$TAG.log | tee -a $O/round_$TAG.log
