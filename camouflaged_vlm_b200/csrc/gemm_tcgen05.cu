@@ -108,7 +108,12 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
 //   CTA (rank 0) issues the MMAs for both; TMA completions of both CTAs land on the leader's "full" barrier,
 //   tcgen05.commit multicasts "empty" / "accumulator full" to both CTAs, and the epilogue warps of both CTAs
 //   hand the accumulator back by arriving on the leader's "accumulator empty" barrier.
-template <bool PAIR>
+// FEAT selects which optional epilogue / scheduling features are compiled in (the plain proj and lin1 GEMMs have no
+// slack in their epilogues: carrying the unused branches cost them 15 % and 3 %, profiles/ncu_gemm_r1l vs r1i):
+//   F_PRODUCER  bf16 copy + row statistics (norm1 fold, fp32 path)      F_CONSUMER  LayerNorm applied to the accumulator
+//   F_RARE      batched mode, |.| output, row-periodic residual (stem / high-pass GEMMs)
+constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4;
+template <bool PAIR, int FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -177,10 +182,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-                const int bidx = tile / ep.tiles_per_batch, tl = tile - bidx * ep.tiles_per_batch;
+                const int bidx = (FEAT & F_RARE) ? tile / ep.tiles_per_batch : 0, tl = tile - bidx * ep.tiles_per_batch;
                 const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM;
                 const int n0 = (tl % tiles_n) * BN + (PAIR ? cta_rank * (BN / 2) : 0);
-                const int bk = bidx * ep.b_k_off;
+                const int bk = (FEAT & F_RARE) ? bidx * ep.b_k_off : 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const bool second = kb >= kblocks1;
@@ -255,14 +260,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         int iter = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
             const int acc = iter & 1;
-            const int bidx = tile / ep.tiles_per_batch, tl = tile - bidx * ep.tiles_per_batch;
+            const int bidx = (FEAT & F_RARE) ? tile / ep.tiles_per_batch : 0, tl = tile - bidx * ep.tiles_per_batch;
             const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM, n0 = (tl % tiles_n) * BN;
             const int row_base = m0 + quad * 32;
-            const long long brow = bidx * ep.batch_rows;          // first output row of this batch entry
+            const long long brow = (FEAT & F_RARE) ? bidx * ep.batch_rows : 0;   // first output row of this batch entry
             // LayerNorm of the A rows, applied to the accumulator (GemmArgs::ln_stat): this lane's 4 rows of the
             // bf16 path.  out = rstd * (acc - mu * colsum) + bias  ==  LN(x) * W^T + b  with gamma folded into W.
             float ln_rs[4] = {1.f, 1.f, 1.f, 1.f}, ln_nm[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ep.ln_rows != nullptr) {
+            if ((FEAT & F_CONSUMER) && ep.ln_rows != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = row_base + 8 * i + (lane >> 2);
@@ -292,7 +297,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                             pb0 = __ldg(reinterpret_cast<const float4*>(bias + col));
                             pb1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
                         }
-                        if (ep.ln_rows != nullptr) {
+                        if ((FEAT & F_CONSUMER) && ep.ln_rows != nullptr) {
                             pc0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col));
                             pc1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + 4));
                         }
@@ -307,7 +312,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         const int row = row_base + 4 * i + (lane >> 3);
                         rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (row < M && col < N) {
-                            const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : brow + row;
+                            const long long rrow = ((FEAT & F_RARE) && ep.res_row_mod > 0) ? row % ep.res_row_mod : brow + row;
                             rr[i] = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                         }
                     }
@@ -348,17 +353,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                             if (use_res) {
                                 x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
                             }
-                            if (ep.act_abs) {
+                            if ((FEAT & F_RARE) && ep.act_abs) {
                                 x.x = fabsf(x.x); x.y = fabsf(x.y); x.z = fabsf(x.z); x.w = fabsf(x.w);
                             }
                             *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (brow + row) * ep.ldo + col) = x;
-                            if (ep.copy_bf16 != nullptr) {
+                            if ((FEAT & F_PRODUCER) && ep.copy_bf16 != nullptr) {
                                 uint2 pk;
                                 pk.x = pack_bf16(x.x, x.y);
                                 pk.y = pack_bf16(x.z, x.w);
                                 *reinterpret_cast<uint2*>(ep.copy_bf16 + static_cast<long long>(row) * ep.ldc + col) = pk;
                             }
-                            if (ep.stat_out != nullptr) {
+                            if ((FEAT & F_PRODUCER) && ep.stat_out != nullptr) {
                                 st1[i] += (x.x + x.y) + (x.z + x.w);
                                 st2[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
                             }
@@ -369,7 +374,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     const int c8 = lane & 3, rsub = lane >> 2;
                     const int col = col0 + c8 * 8;
                     const bool col_ok = col < N;           // N % 8 == 0
-                    const bool use_ln = ep.ln_rows != nullptr;
+                    const bool use_ln = (FEAT & F_CONSUMER) && ep.ln_rows != nullptr;
                     uint64_t bb[4], cs[4];
                     bb[0] = f32x2_pack(pb0.x, pb0.y); bb[1] = f32x2_pack(pb0.z, pb0.w);
                     bb[2] = f32x2_pack(pb1.x, pb1.y); bb[3] = f32x2_pack(pb1.z, pb1.w);
@@ -397,7 +402,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
                             }
                             if (ep.residual) {
-                                const long long rrow = ep.res_row_mod > 0 ? row % ep.res_row_mod : brow + row;
+                                const long long rrow = ((FEAT & F_RARE) && ep.res_row_mod > 0) ? row % ep.res_row_mod : brow + row;
                                 const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                                 const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col + 4);
                                 y[0] = f32x2_add(y[0], f32x2_pack(r0.x, r0.y)); y[1] = f32x2_add(y[1], f32x2_pack(r0.z, r0.w));
@@ -415,7 +420,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 }
                 __syncwarp();   // staging tile is rewritten by the next chunk
             }
-            if (ep.stat_out != nullptr && !ep.out_bf16 && row_base < M && n0 + half * EPI_COLS < N) {
+            if ((FEAT & F_PRODUCER) && ep.stat_out != nullptr && !ep.out_bf16 && row_base < M && n0 + half * EPI_COLS < N) {
                 // (sum, sum of squares) of this warp's 32 rows over its EPI_COLS columns: 8 lanes share a row
                 const int grp = (n0 + half * EPI_COLS) / EPI_COLS;
 #pragma unroll
@@ -524,6 +529,59 @@ static int num_sms() {
     return n;
 }
 
+template <bool PAIR, int FEAT>
+static int launch_kernel(int total_tiles, cudaStream_t stream, const CUtensorMap& tA1, const CUtensorMap& tB1,
+                         const CUtensorMap& tA2, const CUtensorMap& tB2, int kb1, int kb2, int m, int n, int tiles_m,
+                         int tiles_n, const GemmEpi& ep) {
+    auto kern = gemm_bf16_tcgen05_kernel<PAIR, FEAT>;
+    constexpr int smem = PAIR ? GEMM_SMEM_PAIR : GEMM_SMEM;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    if (PAIR) {   // clusters of two CTAs (one TPC): cta_group::2
+        const int clusters = total_tiles < num_sms() / 2 ? total_tiles : num_sms() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVLM_CUDA(cudaLaunchKernelEx(&cfg, kern, tA1, tB1, tA2, tB2, kb1, kb2, m, n, tiles_m, tiles_n, ep));
+    } else {
+        const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+        kern<<<grid, GEMM_THREADS, smem, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, m, n, tiles_m, tiles_n, ep);
+    }
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
+template <typename... Args>
+static int launch_variant(bool pair, int feat, Args&&... args) {
+    constexpr int ALL = F_PRODUCER | F_CONSUMER | F_RARE;
+    if (pair) {
+        switch (feat) {
+            case 0: return launch_kernel<true, 0>(args...);
+            case F_PRODUCER: return launch_kernel<true, F_PRODUCER>(args...);
+            case F_CONSUMER: return launch_kernel<true, F_CONSUMER>(args...);
+            default: return launch_kernel<true, ALL>(args...);
+        }
+    }
+    switch (feat) {
+        case 0: return launch_kernel<false, 0>(args...);
+        case F_PRODUCER: return launch_kernel<false, F_PRODUCER>(args...);
+        case F_CONSUMER: return launch_kernel<false, F_CONSUMER>(args...);
+        default: return launch_kernel<false, ALL>(args...);
+    }
+}
+
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (!a.a1 || !a.b1 || !a.out) return set_error(CVLM_ERR_ARG, "gemm: null operand");
     if (a.m <= 0 || a.n <= 0 || a.k1 <= 0) return set_error(CVLM_ERR_ARG, "gemm: bad shape m=%d n=%d k=%d", a.m, a.n, a.k1);
@@ -557,59 +615,31 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         tA2 = tA1;
         tB2 = tB1;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-
-        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        CVLM_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_PAIR));
-        attr_set = true;
-    }
-    const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     if ((a.copy_bf16 || a.stat_out) && a.out_bf16)
         return set_error(CVLM_ERR_ARG, "gemm: bf16 copy / row statistics need the fp32 output path");
     if (a.copy_bf16 && ((reinterpret_cast<uintptr_t>(a.copy_bf16) & 7) || (a.ldc % 4)))
         return set_error(CVLM_ERR_ARG, "gemm: bf16 copy must allow 8-byte vectors");
+    if (a.copy_bf16 && (a.copy_bf16 == a.a1 || a.copy_bf16 == a.a2))
+        return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
     if (a.stat_out && a.stat_groups != (a.n + EPI_COLS - 1) / EPI_COLS)
         return set_error(CVLM_ERR_ARG, "gemm: stat_groups must be ceil(n / %d)", EPI_COLS);
     if (a.ln_rows && (!a.out_bf16 || !a.ln_colsum || (reinterpret_cast<uintptr_t>(a.ln_colsum) & 15) ||
                       (reinterpret_cast<uintptr_t>(a.ln_rows) & 7)))
         return set_error(CVLM_ERR_ARG, "gemm: the LayerNorm epilogue needs bf16 output, column sums and finalized row statistics");
-    if (a.copy_bf16 && (a.copy_bf16 == a.a1 || a.copy_bf16 == a.a2))
-        return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
                static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
                reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
                a.act_abs};
+    const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     const int tiles_n = (a.n + BN - 1) / BN;
-    if (pair) {
-        const int tiles_m = (a.m + 2 * BM - 1) / (2 * BM);
-        ep.tiles_per_batch = tiles_m * tiles_n;
-        const int total_tiles = nbatch * tiles_m * tiles_n;
-        const int clusters = total_tiles < num_sms() / 2 ? total_tiles : num_sms() / 2;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(GEMM_THREADS);
-        cfg.dynamicSmemBytes = GEMM_SMEM_PAIR;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CVLM_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<true>, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n,
-                                     nbatch * tiles_m, tiles_n, ep));
-    } else {
-        const int tiles_m = (a.m + BM - 1) / BM;
-        ep.tiles_per_batch = tiles_m * tiles_n;
-        const int total_tiles = nbatch * tiles_m * tiles_n;
-        const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-        gemm_bf16_tcgen05_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n,
-                                                                             nbatch * tiles_m, tiles_n, ep);
-    }
-    CVLM_CUDA(cudaGetLastError());
-    return CVLM_OK;
+    const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;
+    ep.tiles_per_batch = tiles_m * tiles_n;
+    const int total_tiles = nbatch * tiles_m * tiles_n;
+    // the smallest feature set that covers this call; anything that mixes sets takes the generic kernel
+    int feat = ((a.copy_bf16 || a.stat_out) ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0) |
+               ((nbatch > 1 || a.act_abs || a.res_row_mod > 0) ? F_RARE : 0);
+    if (feat != 0 && feat != F_PRODUCER && feat != F_CONSUMER) feat = F_PRODUCER | F_CONSUMER | F_RARE;
+    return launch_variant(pair, feat, total_tiles, stream, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, nbatch * tiles_m, tiles_n, ep);
 }
 
 }  // namespace cvlm
