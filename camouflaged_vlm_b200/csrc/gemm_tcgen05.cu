@@ -112,7 +112,9 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
 // slack in their epilogues: carrying the unused branches cost them 15 % and 3 %, profiles/ncu_gemm_r1l vs r1i):
 //   F_PRODUCER  bf16 copy + row statistics (norm1 fold, fp32 path)      F_CONSUMER  LayerNorm applied to the accumulator
 //   F_RARE      batched mode, |.| output, row-periodic residual (stem / high-pass GEMMs)
-constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4;
+//   F_STATIC    the epilogue type is a compile-time fact: F_BF16 (bf16 output), F_GELU, F_RES (fp32 residual) say which;
+//               without it those three are read from GemmEpi at run time (stem / adapter / neck GEMMs)
+constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64;
 template <bool PAIR, int FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -252,6 +254,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         // active on the K=1280 GEMMs).  Each warp therefore transposes its 32x32 fp32 chunk through a
         // private, XOR-swizzled 4 KB shared-memory tile so that global loads/stores run along rows:
         // 8 lanes x 16 B = one full 128-byte line of the fp32 output / residual per row.
+        const bool out_bf16 = (FEAT & F_STATIC) ? (FEAT & F_BF16) != 0 : ep.out_bf16 != 0;
+        const bool act_gelu = (FEAT & F_STATIC) ? (FEAT & F_GELU) != 0 : ep.act_gelu != 0;
+        const bool has_res = (FEAT & F_STATIC) ? (FEAT & F_RES) != 0 : ep.residual != nullptr;
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
         const int half = ew >> 2;           // which EPI_COLS of the 256 accumulator columns
@@ -290,7 +295,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 // bf16 path: this lane's 8 bias / column-sum values, requested before the TMEM load and the transpose
                 // so that their latency is off the critical path
                 float4 pb0 = make_float4(0.f, 0.f, 0.f, 0.f), pb1 = pb0, pc0 = pb0, pc1 = pb0;
-                if (ep.out_bf16) {
+                if (out_bf16) {
                     const int col = col0 + (lane & 3) * 8;
                     if (col < N) {
                         if (bias) {
@@ -304,7 +309,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     }
                 }
                 float4 rr[8];
-                const bool use_res = ep.residual != nullptr && !ep.out_bf16;
+                const bool use_res = has_res && !out_bf16;
                 if (use_res) {
                     const int col = col0 + (lane & 7) * 4;
 #pragma unroll
@@ -334,7 +339,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 for (int q = 0; q < 8; ++q)
                     st_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
-                if (!ep.out_bf16) {
+                if (!out_bf16) {
                     const int cq = lane & 7, rsub = lane >> 3;
                     const int col = col0 + cq * 4;
                     const bool col_ok = col < N;           // N % 8 == 0: groups of 4 are all-or-nothing
@@ -347,7 +352,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         float4 x = ld_shared_f4(stg + r * 128 + ((cq ^ (r & 7)) << 4));
                         if (row < M && col_ok) {
                             x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                            if (ep.act_gelu) {
+                            if (act_gelu) {
                                 x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
                             }
                             if (use_res) {
@@ -397,11 +402,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
                             }
-                            if (ep.act_gelu) {
+                            if (act_gelu) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
                             }
-                            if (ep.residual) {
+                            if (has_res) {
                                 const long long rrow = ((FEAT & F_RARE) && ep.res_row_mod > 0) ? row % ep.res_row_mod : brow + row;
                                 const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col);
                                 const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col + 4);
@@ -420,7 +425,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 }
                 __syncwarp();   // staging tile is rewritten by the next chunk
             }
-            if ((FEAT & F_PRODUCER) && ep.stat_out != nullptr && !ep.out_bf16 && row_base < M && n0 + half * EPI_COLS < N) {
+            if ((FEAT & F_PRODUCER) && ep.stat_out != nullptr && !out_bf16 && row_base < M && n0 + half * EPI_COLS < N) {
                 // (sum, sum of squares) of this warp's 32 rows over its EPI_COLS columns: 8 lanes share a row
                 const int grp = (n0 + half * EPI_COLS) / EPI_COLS;
 #pragma unroll
@@ -563,22 +568,30 @@ static int launch_kernel(int total_tiles, cudaStream_t stream, const CUtensorMap
     return CVLM_OK;
 }
 
+// The four GEMMs of a transformer block get fully specialised kernels; everything else runs a variant that reads the
+// epilogue type at run time.
+constexpr int V_QKV = F_STATIC | F_BF16 | F_CONSUMER;           // norm1 + qkv
+constexpr int V_PROJ = F_STATIC | F_RES;                        // proj + shortcut
+constexpr int V_LIN1 = F_STATIC | F_BF16 | F_GELU;              // lin1 + GELU
+constexpr int V_LIN2 = F_STATIC | F_RES | F_PRODUCER;           // lin2 + shortcut, feeds the next norm1
+constexpr int V_ANY = F_PRODUCER | F_CONSUMER | F_RARE;         // run-time epilogue type, every feature
 template <typename... Args>
 static int launch_variant(bool pair, int feat, Args&&... args) {
-    constexpr int ALL = F_PRODUCER | F_CONSUMER | F_RARE;
     if (pair) {
         switch (feat) {
-            case 0: return launch_kernel<true, 0>(args...);
-            case F_PRODUCER: return launch_kernel<true, F_PRODUCER>(args...);
-            case F_CONSUMER: return launch_kernel<true, F_CONSUMER>(args...);
-            default: return launch_kernel<true, ALL>(args...);
+            case V_QKV: return launch_kernel<true, V_QKV>(args...);
+            case V_PROJ: return launch_kernel<true, V_PROJ>(args...);
+            case V_LIN1: return launch_kernel<true, V_LIN1>(args...);
+            case V_LIN2: return launch_kernel<true, V_LIN2>(args...);
+            default: return launch_kernel<true, V_ANY>(args...);
         }
     }
     switch (feat) {
-        case 0: return launch_kernel<false, 0>(args...);
-        case F_PRODUCER: return launch_kernel<false, F_PRODUCER>(args...);
-        case F_CONSUMER: return launch_kernel<false, F_CONSUMER>(args...);
-        default: return launch_kernel<false, ALL>(args...);
+        case V_QKV: return launch_kernel<false, V_QKV>(args...);
+        case V_PROJ: return launch_kernel<false, V_PROJ>(args...);
+        case V_LIN1: return launch_kernel<false, V_LIN1>(args...);
+        case V_LIN2: return launch_kernel<false, V_LIN2>(args...);
+        default: return launch_kernel<false, V_ANY>(args...);
     }
 }
 
@@ -635,10 +648,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;
     ep.tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = nbatch * tiles_m * tiles_n;
-    // the smallest feature set that covers this call; anything that mixes sets takes the generic kernel
-    int feat = ((a.copy_bf16 || a.stat_out) ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0) |
-               ((nbatch > 1 || a.act_abs || a.res_row_mod > 0) ? F_RARE : 0);
-    if (feat != 0 && feat != F_PRODUCER && feat != F_CONSUMER) feat = F_PRODUCER | F_CONSUMER | F_RARE;
+    // the exact shape of this call's epilogue; launch_variant maps the four block GEMMs to their own kernels
+    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0;
+    const bool producer = a.copy_bf16 != nullptr && a.stat_out != nullptr;
+    int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.residual ? F_RES : 0) |
+               (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0);
+    if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || !a.bias) feat = V_ANY;
     return launch_variant(pair, feat, total_tiles, stream, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, nbatch * tiles_m, tiles_n, ep);
 }
 
