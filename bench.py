@@ -304,19 +304,16 @@ def run_ours(args):
     if not args.skip_e2e:
         x_host = torch.empty(B, cfg.in_chans, cfg.img_size, cfg.img_size, pin_memory=True)
         x_host.copy_(x_dev)
-        out_host = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
-
-        def gather(emb):                                        # embeddings gathered over NVLink (configs[2])
-            if world == 1:
-                return emb
-            full = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev)
-            dist.all_gather_into_tensor(full, emb)
-            return full
+        out_host = torch.empty(B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
+        gathered = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev) if world > 1 else None
 
         def e2e_step():
-            # the public host-buffer call: chunked H2D on a copy stream under the encoder, (all-gather,) D2H
+            # the public host-buffer call: chunked H2D on a copy stream under the encoder, D2H of this rank's
+            # embeddings per chunk; at N > 1 the embeddings are also all-gathered on the devices (configs[2])
             with torch.no_grad():
-                model.forward_host(x_host, out_host=out_host, chunk=8, gather=gather if world > 1 else None, interm=interm)
+                res = model.forward_host(x_host, out_host=out_host, chunk=8, interm=interm, return_device=world > 1)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, res[1])
 
         e2e_step()
         barrier()
@@ -332,8 +329,7 @@ def run_ours(args):
                "note": "ImageEncoderViT.forward_host: pinned host -> device in chunks of 8 on a copy stream under "
                        "forward(x, interm) of the previous chunk, "
                        + ("NCCL all_gather_into_tensor of the embeddings, " if world > 1 else "")
-                       + "device -> pinned host copy of the embeddings; whole-job bytes (every rank copies the "
-                         "gathered embeddings out)"}
+                       + "device -> pinned host copy of each rank's embeddings (per chunk, same copy stream); whole-job bytes"}
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None

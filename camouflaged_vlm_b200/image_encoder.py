@@ -303,14 +303,14 @@ class ImageEncoderViT(nn.Module):
 
     @torch.no_grad()
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunk: int = 8,
-                     gather: Optional[Any] = None, interm: bool = False):
+                     interm: bool = False, return_device: bool = False):
         """Embeddings for a batch that lives in HOST memory (``x_host`` fp32 [B,3,S,S], ideally pinned): the batch is
-        cut into chunks of ``chunk`` images and the host->device copy of chunk i+1 and the device->host copy of the
+        cut into chunks of ``chunk`` images; the host->device copy of chunk i+1 and the device->host copy of the
         embeddings of chunk i-1 run on a copy stream underneath the encoder of chunk i (two device staging buffers).
-        ``gather`` (optional) maps the device embeddings of the whole batch to what should be copied out, e.g.
-        ``dist.gather_embeddings``.  Returns ``out_host`` ([B,out,g,g] fp32, pinned if allocated here), valid once the
-        current stream has been synchronised; with ``interm=True`` also the list of per-global-block embeddings, which
-        stay on the device (NCHW views, like ``forward``)."""
+        Returns ``out_host`` ([B,out,g,g] fp32, pinned if allocated here), valid once the current stream has been
+        synchronised.  ``return_device=True`` appends the device copy of the embeddings (e.g. to all-gather them
+        across ranks, ``dist.gather_embeddings``); ``interm=True`` appends the list of per-global-block embeddings,
+        which stay on the device (NCHW views, like ``forward``)."""
         cfg = self._cfg
         if x_host.is_cuda:
             raise ValueError("forward_host takes a host tensor; call the module directly for device tensors")
@@ -340,7 +340,7 @@ class ImageEncoderViT(nn.Module):
                 stage[i % 2][:e - s].copy_(x_host[s:e], non_blocking=True)
                 ready[i % 2].record(cs)
 
-        if gather is None and out_host is None:
+        if out_host is None:
             out_host = torch.empty(B, cfg.out_chans, g, g, dtype=torch.float32, pin_memory=True)
         upload(0)
         for i, (s, e) in enumerate(spans):
@@ -349,20 +349,16 @@ class ImageEncoderViT(nn.Module):
             main.wait_event(ready[i % 2])
             self._run(stage[i % 2][:e - s], emb[s:e], [t[s:e] for t in interms])
             free[i % 2].record(main)
-            if gather is None:                      # this chunk's embeddings go out under the next chunk's encoder
-                with torch.cuda.stream(cs):
-                    cs.wait_event(free[i % 2])
-                    out_host[s:e].copy_(emb[s:e], non_blocking=True)
-        if gather is None:
-            main.wait_stream(cs)
-        else:
-            result = gather(emb)
-            if out_host is None:
-                out_host = torch.empty(tuple(result.shape), dtype=torch.float32, pin_memory=True)
-            out_host.copy_(result, non_blocking=True)
+            with torch.cuda.stream(cs):             # this chunk's embeddings go out under the next chunk's encoder
+                cs.wait_event(free[i % 2])
+                out_host[s:e].copy_(emb[s:e], non_blocking=True)
+        main.wait_stream(cs)
+        ret = [out_host]
+        if return_device:
+            ret.append(emb)
         if interm:
-            return out_host, [t.permute(0, 3, 1, 2) for t in interms]
-        return out_host
+            ret.append([t.permute(0, 3, 1, 2) for t in interms])
+        return ret[0] if len(ret) == 1 else tuple(ret)
 
     @torch.no_grad()
     def forward_partial(self, x: torch.Tensor, stop_after_block: int) -> torch.Tensor:
