@@ -85,6 +85,9 @@ _SIGS = {
     "cvlm_op_im2col_patch16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvlm_op_im2col_3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvlm_op_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_op_preprocess_u8_scratch_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),
+    "cvlm_op_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_op_high_pass_scratch_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),
     "cvlm_op_high_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_longlong, C.c_void_p]),

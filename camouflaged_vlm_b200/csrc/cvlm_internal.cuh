@@ -80,6 +80,10 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, void
 int ln_finalize_launch(const float* partial, int groups, int width, float eps, float* rows_out, long long rows,
                        cudaStream_t stream);
 int cast_bf16_launch(const float* x, void* out, long long n, cudaStream_t stream);
+// ---- image input pipeline (preprocess.cu)
+long long preprocess_scratch_bytes(int h, int w, int out_size);
+int preprocess_u8_launch(const unsigned char* img, int h, int w, float* out, int out_size, const float* mean, const float* stdv,
+                         void* scratch, long long scratch_bytes, cudaStream_t stream);
 // ---- high-pass filter of the adapter (highpass.cu)
 long long high_pass_scratch_bytes(int batch, int chans, int img_size);
 int high_pass_launch(const float* images, float* out, int batch, int chans, int img_size, const void* pcat,

@@ -516,6 +516,16 @@ int cvlm_op_ln_finalize(const float* partial, int groups, int width, float eps, 
     return ln_finalize_launch(partial, groups, width, eps, rows_out, rows, static_cast<cudaStream_t>(stream));
 }
 
+long long cvlm_op_preprocess_u8_scratch_bytes(int h, int w, int out_size) {
+    if (h <= 0 || w <= 0 || out_size <= 0) return set_error(CVLM_ERR_ARG, "preprocess_u8_scratch_bytes: bad argument");
+    return preprocess_scratch_bytes(h, w, out_size);
+}
+
+int cvlm_op_preprocess_u8(const unsigned char* img, int h, int w, float* out, int out_size, const float* mean,
+                          const float* std, void* scratch, long long scratch_bytes, cvlm_stream_t stream) {
+    return preprocess_u8_launch(img, h, w, out, out_size, mean, std, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
 long long cvlm_op_high_pass_scratch_bytes(int batch, int chans, int img_size) {
     if (batch <= 0 || chans <= 0 || img_size <= 0) return set_error(CVLM_ERR_ARG, "high_pass_scratch_bytes: bad argument");
     return high_pass_scratch_bytes(batch, chans, img_size);

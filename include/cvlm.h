@@ -167,6 +167,13 @@ long long cvlm_op_high_pass_scratch_bytes(int batch, int chans, int img_size);
 int cvlm_op_high_pass(const float* images, float* out, int batch, int chans, int img_size, const void* pcat,
                       const void* npr, const void* pi, void* scratch, long long scratch_bytes, cvlm_stream_t stream);
 
+/* The reference's image input pipeline (datasets/wrappers.py:22-27: transforms.Resize((S,S)) on a PIL image ->
+ * ToTensor -> Normalize), bit-exact: img uint8 HWC [h, w, 3] (device) -> out fp32 [3, out_size, out_size] (device).
+ * mean / std: 3 host floats each.  scratch: device bytes >= cvlm_op_preprocess_u8_scratch_bytes, 16-byte aligned. */
+long long cvlm_op_preprocess_u8_scratch_bytes(int h, int w, int out_size);
+int cvlm_op_preprocess_u8(const unsigned char* img, int h, int w, float* out, int out_size, const float* mean,
+                          const float* std, void* scratch, long long scratch_bytes, cvlm_stream_t stream);
+
 /* t = bf16(hand + cst + W_eg * scramble(x0)); see rowops.cu / DESIGN.md "adapter". */
 int cvlm_op_adapter_embed(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,
                           int batch, int tokens, int dim, int rank, int rank_pad, cvlm_stream_t stream);
