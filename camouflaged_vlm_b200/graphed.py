@@ -1,0 +1,42 @@
+"""CUDA-graph replay of the encoder for a fixed batch size (latency path, e.g. the reference's batch-1 demo).
+
+One forward is 243 dependent kernel launches; replayed from a graph the gaps between them shrink (measured on a B200,
+tools/graph_probe.py: batch 1: 7.84 -> 7.42 ms, batch 8: 47.8 -> 46.3 ms, bit-identical outputs).  A graph bakes its
+buffers in, so this is an explicit wrapper with static-buffer semantics rather than something ``forward`` does silently:
+the tensors it returns are overwritten by the next call."""
+from typing import List, Tuple, Union
+
+import torch
+
+from .image_encoder import ImageEncoderViT
+
+
+class GraphedEncoder:
+    def __init__(self, model: ImageEncoderViT, batch: int, interm: bool = False):
+        cfg = model.config
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedEncoder needs the model on a CUDA device")
+        self.model, self.batch, self.interm = model, batch, interm
+        self.static_x = torch.zeros(batch, cfg.in_chans, cfg.img_size, cfg.img_size, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():          # warm-up outside the capture: weight packing,
+            model(self.static_x, interm=interm)                 # workspace, cudaFuncSetAttribute, tensor-map cache
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = model(self.static_x, interm=interm)
+        self._weights_key = model._packed_key
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> Union[torch.Tensor, Tuple[torch.Tensor, List[torch.Tensor]]]:
+        """``x``: [batch, 3, S, S] on the model's device.  Returns the graph's static output tensors (valid until the
+        next call)."""
+        if tuple(x.shape) != tuple(self.static_x.shape):
+            raise ValueError(f"captured for input {tuple(self.static_x.shape)}, got {tuple(x.shape)}")
+        if self.model._weights_key(self.static_x.device) != self._weights_key:
+            raise RuntimeError("the model's parameters changed after capture: build a new GraphedEncoder")
+        self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

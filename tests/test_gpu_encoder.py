@@ -159,3 +159,20 @@ def test_forward_host_pipelines_chunks_and_matches_forward():
         got = m.forward_host(x.pin_memory(), chunk=2)
     torch.cuda.synchronize()
     assert got.is_pinned() and torch.equal(got, want.cpu())
+
+
+def test_graphed_encoder_replays_bit_identically():
+    """CUDA-graph replay (camouflaged_vlm_b200.graphed): same bits as the eager forward, new inputs each call."""
+    from camouflaged_vlm_b200.graphed import GraphedEncoder
+    cfg = PRESETS["tiny"]
+    m = _encoder(cfg)
+    ge = GraphedEncoder(m, batch=2, interm=True)
+    for seed in (0, 1):
+        x = seeded_images(cfg, 2, seed).cuda()
+        with torch.no_grad():
+            want, want_i = m(x, interm=True)
+        got, got_i = ge(x)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want) and all(torch.equal(a, b) for a, b in zip(got_i, want_i))
+    with pytest.raises(ValueError):
+        ge(seeded_images(cfg, 1).cuda())
