@@ -9,7 +9,7 @@ echo "=== tests" | tee $O/round_$TAG.log
 timeout 900 python -m pytest -q -m gpu tests/ 2>&1 | tail -15 | tee -a $O/round_$TAG.log
 if fault $O/round_$TAG.log; then echo "fault in tests, stopping"; exit 3; fi
 echo "=== parity" | tee -a $O/round_$TAG.log
-timeout 600 python tools/parity_report.py $O/parity_$TAG.json 2>&1 | tail -8 | tee -a $O/round_$TAG.log
+timeout 600 python tests/parity_report.py $O/parity_$TAG.json 2>&1 | tail -8 | tee -a $O/round_$TAG.log
 echo "=== smoke" | tee -a $O/round_$TAG.log
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee -a $O/round_$TAG.log
 echo "=== bench" | tee -a $O/round_$TAG.log
