@@ -229,3 +229,30 @@ def test_high_pass_native(batch, n):
     assert _rel(got, want) < 5e-3
     # images are independent: a batch of one gives the same bits
     assert torch.equal(ops.high_pass(x[:1].contiguous(), pcat, npr, pi), got[:1])
+
+
+def test_gemm_random_shapes(gemm_mode):
+    """Seeded sweep over ragged shapes (every M / N / K edge case of the tile, pair and batch logic) with random
+    epilogue combinations, against fp32 torch."""
+    import random
+    rnd = random.Random(1234)
+    for it in range(24):
+        m = rnd.choice([1, 7, 127, 128, 129, 255, 256, 257, 300, 513, 1000, 2049])
+        n = 8 * rnd.randint(1, 90)
+        k = 8 * rnd.randint(1, 100)
+        a = _randn(m, k, seed=100 + it, dtype=torch.bfloat16)
+        b = _randn(n, k, seed=200 + it, dtype=torch.bfloat16, scale=0.05)
+        bias = _randn(n, seed=300 + it) if rnd.random() < 0.7 else None
+        res = _randn(m, n, seed=400 + it) if rnd.random() < 0.5 else None
+        gelu = rnd.random() < 0.3
+        want = a.float() @ b.float().t()
+        if bias is not None:
+            want = want + bias
+        if gelu:
+            want = torch.nn.functional.gelu(want)
+        if res is not None:
+            want = want + res
+        got = ops.gemm_bf16(a, b, bias=bias, residual=res, gelu=gelu)
+        assert _rel(got, want) < 2e-5, (it, m, n, k, gelu)
+        got16 = ops.gemm_bf16(a, b, bias=bias, residual=res, gelu=gelu, out_dtype=torch.bfloat16)
+        assert _rel(got16.float(), want) < 4e-3, (it, m, n, k, gelu)
