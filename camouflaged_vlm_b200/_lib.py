@@ -35,6 +35,13 @@ class EncoderConfigC(C.Structure):
     ]
 
 
+class DecoderConfigC(C.Structure):
+    """struct cvlm_decoder_config (include/cvlm.h)."""
+    _fields_ = [("dim", C.c_int), ("heads", C.c_int), ("mlp_dim", C.c_int), ("depth", C.c_int),
+                ("num_mask_tokens", C.c_int), ("grid", C.c_int), ("cond_tokens", C.c_int),
+                ("ln_eps", C.c_float), ("ln2d_eps", C.c_float)]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into libcvlm_b200.so (no GPU needed)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
@@ -93,6 +100,15 @@ _SIGS = {
                                     C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_op_adapter_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvlm_decoder_create": (C.c_int, [C.POINTER(DecoderConfigC), C.POINTER(C.c_void_p)]),
+    "cvlm_decoder_destroy": (C.c_int, [C.c_void_p]),
+    "cvlm_decoder_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
+    "cvlm_decoder_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "cvlm_decoder_last_launches": (C.c_longlong, [C.c_void_p]),
+    "cvlm_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_op_bilinear_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -1,0 +1,984 @@
+// Mask decoder runtime: MaskDecoder_Edge.forward / predict_masks
+// (models/mmseg/models/sam/mask_decoder_edge.py:96-190) with TwoWayTransformer_MaskDecoder_Edge
+// (transformer_maskdecoder_edge.py:62-214), batched over images -- the reference only works at batch 1
+// (repeat_interleave of the embeddings by the prompt batch), here image b is decoded with prompt b.
+//
+// Split of the work
+//   image side  (4096 keys x 256 per image, and the 128^2 / 256^2 up-scaling maps): every projection, both transposed
+//               convolutions (k2 s2: four GEMM column groups per input pixel) and both 3x3 convolutions (im2col) run on
+//               the tcgen05 GEMM (gemm_tcgen05.cu) with bf16 operands and fp32 accumulation; `keys` stays fp32.
+//   token side  (6 output tokens + the prompt tokens per image): one CTA per image runs a whole transformer layer in
+//               fp32 (self attention, token->image attention over the 4096 keys, token->prompt attention, MLP, and the
+//               key / value projections the image side needs next).
+//
+// Data layout in HBM for a chunk of B images (T = g*g, M = B*T; P1 = 4M, P2 = 16M pixels of the up-scaled maps):
+//   keys  fp32 [M,256]   image tokens (NHWC), updated in place by the out_proj epilogues + LayerNorm
+//   kb    bf16 [M,256]   keys;   kpb bf16 [M,256]  keys + image_pe;   eb bf16 [M,256]  the raw embedding
+//   kimg / vimg / qi  fp32 [M,128]   projections for the cross attentions;  ao bf16 [M,128] attention output
+//   Up-scaled maps keep NESTED pixel order: pixel (y,x) of the g x g map owns the contiguous rows
+//   ((y*g+x)*4 + s1)*4 + s2, s = 2*dy+dx of each transposed convolution, so a k2 s2 transposed convolution is a plain
+//   reshape of the GEMM output.  im2col and the final mask kernel translate to raster order.
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+
+#include "cvlm_internal.cuh"
+
+struct cvlm_decoder {
+    cvlm_decoder_config cfg;
+    std::unordered_map<std::string, std::pair<const void*, long long>> tensors;
+    long long last_launches = 0;
+};
+
+namespace cvlm {
+
+namespace {
+
+constexpr int DD = 256;        // transformer_dim
+constexpr int DI = 128;        // inner width of the cross attentions (attention_downsample_rate 2)
+constexpr int NH = 8;          // heads
+constexpr int NTOK = 6;        // iou token, 4 mask tokens, edge token (mask_decoder_edge.py:157)
+constexpr int NMASK = 4;
+constexpr int MAXC = 8;        // prompt tokens per image supported by the kernels
+constexpr int DQ = 64, DE = 32;
+constexpr int TOK_THREADS = 512;
+
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prep: NCHW -> token-major.  keys = emb + dense, kb = bf16(keys), kpb = bf16(keys + pe), eb = bf16(emb), pos_t = pe.
+// One CTA per 32 tokens of one image; the 256 x 32 tile goes through shared memory three times (emb, dense, pe).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_prep_kernel(const float* __restrict__ emb, const float* __restrict__ dense,
+                                                       long long dense_bstride, const float* __restrict__ pe,
+                                                       float* __restrict__ keys, __nv_bfloat16* __restrict__ kb,
+                                                       __nv_bfloat16* __restrict__ kpb, __nv_bfloat16* __restrict__ eb,
+                                                       float* __restrict__ pos_t, int T) {
+    __shared__ float tile[DD][33];
+    const int b = blockIdx.y, t0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float val[4][8];
+    auto load = [&](const float* src) {
+        __syncthreads();
+        for (int c = warp; c < DD; c += 8) tile[c][lane] = src[static_cast<long long>(c) * T + t0 + lane];
+        __syncthreads();
+    };
+    load(emb + static_cast<long long>(b) * DD * T);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long row = static_cast<long long>(b) * T + t0 + warp * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            val[i][j] = tile[lane + 32 * j][warp * 4 + i];
+            eb[row * DD + lane + 32 * j] = __float2bfloat16_rn(val[i][j]);
+        }
+    }
+    load(dense + static_cast<long long>(b) * dense_bstride);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long row = static_cast<long long>(b) * T + t0 + warp * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            val[i][j] = __fadd_rn(val[i][j], tile[lane + 32 * j][warp * 4 + i]);
+            keys[row * DD + lane + 32 * j] = val[i][j];
+            kb[row * DD + lane + 32 * j] = __float2bfloat16_rn(val[i][j]);
+        }
+    }
+    load(pe);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long row = static_cast<long long>(b) * T + t0 + warp * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p = tile[lane + 32 * j][warp * 4 + i];
+            kpb[row * DD + lane + 32 * j] = __float2bfloat16_rn(__fadd_rn(val[i][j], p));
+            if (b == 0) pos_t[static_cast<long long>(t0 + warp * 4 + i) * DD + lane + 32 * j] = p;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row LayerNorm over C channels (nn.LayerNorm of the transformer, LayerNorm2d of the up-scaling stacks: both are
+// (x - mean) / sqrt(var + eps) * w + b over the channel vector of one pixel), optional GELU, one warp per row.
+// Outputs (each optional): fp32, bf16, bf16 of (result + pos[row % T]).  In place on x is allowed.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, int gelu,
+                                                          const float* __restrict__ pos, int T, float* out_f32,
+                                                          __nv_bfloat16* __restrict__ out_b16,
+                                                          __nv_bfloat16* __restrict__ out_pos_b16, long long rows) {
+    constexpr int PER = C / 32;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        v[j] = x[row * C + lane + 32 * j];
+        s += v[j];
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        v[j] -= mean;
+        q = fmaf(v[j], v[j], q);
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int c = lane + 32 * j;
+        float y = fmaf(v[j] * rstd, gamma[c], beta[c]);
+        if (gelu) y = gelu_exact(y);
+        if (out_f32) out_f32[row * C + c] = y;
+        if (out_b16) out_b16[row * C + c] = __float2bfloat16_rn(y);
+        if (out_pos_b16) out_pos_b16[row * C + c] = __float2bfloat16_rn(y + pos[(row % T) * C + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Image -> token / image -> prompt attention (Attention.forward with 4096 queries and nk <= 8 keys): one thread per
+// (image token, head), 16 channels per head.  q fp32 [M,128]; kt / vt fp32 [B, nk, 128]; out bf16 [M,128].
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_few_key_attn_kernel(const float* __restrict__ q, const float* __restrict__ kt,
+                                                               const float* __restrict__ vt, int nk,
+                                                               __nv_bfloat16* __restrict__ out, int T) {
+    __shared__ float ks[MAXC][DI], vs[MAXC][DI];
+    const long long row0 = static_cast<long long>(blockIdx.x) * 32;
+    const int b = static_cast<int>(row0 / T);
+    for (int i = threadIdx.x; i < nk * DI; i += 256) {
+        ks[i / DI][i % DI] = kt[static_cast<long long>(b) * nk * DI + i];
+        vs[i / DI][i % DI] = vt[static_cast<long long>(b) * nk * DI + i];
+    }
+    __syncthreads();
+    const int h = threadIdx.x & 7;
+    const long long row = row0 + (threadIdx.x >> 3);
+    float qv[16];
+    const float4* qp = reinterpret_cast<const float4*>(q + row * DI + h * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 t = qp[i];
+        qv[4 * i] = t.x; qv[4 * i + 1] = t.y; qv[4 * i + 2] = t.z; qv[4 * i + 3] = t.w;
+    }
+    float lg[MAXC], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+        lg[j] = -INFINITY;
+        if (j < nk) {
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) s = fmaf(qv[d], ks[j][h * 16 + d], s);
+            lg[j] = s * 0.25f;     // 1 / sqrt(16)
+            mx = fmaxf(mx, lg[j]);
+        }
+    }
+    float l = 0.f, acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+        if (j < nk) {
+            const float p = expf(lg[j] - mx);
+            l += p;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[d] = fmaf(p, vs[j][h * 16 + d], acc[d]);
+        }
+    }
+    const float inv = 1.f / l;
+    __nv_bfloat162 o[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] = __floats2bfloat162_rn(acc[2 * d] * inv, acc[2 * d + 1] * inv);
+    uint4* op = reinterpret_cast<uint4*>(out + row * DI + h * 16);
+    op[0] = *reinterpret_cast<uint4*>(&o[0]);
+    op[1] = *reinterpret_cast<uint4*>(&o[4]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Token side.  Helpers run with the whole CTA (TOK_THREADS threads); activations live in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+struct AttnW {           // one Attention module (transformer_maskdecoder_edge.py:217-272), fp32 parameters
+    const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob;
+};
+struct NormW {
+    const float *w, *b;
+};
+struct LayerW {
+    AttnW self_attn, t2i, t2c, i2t, i2c;
+    NormW n1, n2, n2c, n3;
+    const float *l1w, *l1b, *l2w, *l2b;
+    int mlp_dim;
+};
+struct Mlp3W {
+    const float *w0, *b0, *w1, *b1, *w2, *b2;
+};
+struct FinalW {
+    AttnW t2i;
+    NormW nf;
+    Mlp3W hyper[NMASK + 1];   // output_hypernetworks_mlps[0..3], edge_mlp
+    Mlp3W iou;
+};
+
+// ys[t][o] = act(sum_k xs[t][k] * W[o][k] + b[o]) for t < NT;  `in` is a multiple of 128 floats
+template <int NT>
+__device__ void tok_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* xs, int ldx, int in,
+                           float* ys, int ldy, int out, bool relu) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < out; o += nw) {
+        float acc[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(W + static_cast<long long>(o) * in);
+        for (int k4 = lane; k4 < in / 4; k4 += 32) {
+            const float4 w = __ldg(wr + k4);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + 4 * k4);
+                acc[t] = fmaf(xv.x, w.x, acc[t]);
+                acc[t] = fmaf(xv.y, w.y, acc[t]);
+                acc[t] = fmaf(xv.z, w.z, acc[t]);
+                acc[t] = fmaf(xv.w, w.w, acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = warp_sum(acc[t]);
+        if (lane == 0) {
+            const float bv = bias ? bias[o] : 0.f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float y = acc[t] + bv;
+                ys[t * ldy + o] = relu ? fmaxf(y, 0.f) : y;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// dst[t][:] = LayerNorm(a[t][:] + (r ? r[t][:] : 0)) over 256 channels, eps 1e-5 (nn.LayerNorm default); one warp per token
+__device__ void tok_add_ln(float* dst, const float* a, const float* r, NormW n, float eps, int nt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nt) {
+        float v[8], s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            v[j] = a[warp * DD + c] + (r ? r[warp * DD + c] : 0.f);
+            s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.f / DD);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] -= mean;
+            q = fmaf(v[j], v[j], q);
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / DD) + eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            dst[warp * DD + c] = fmaf(v[j] * rstd, n.w[c], n.b[c]);
+        }
+    }
+    __syncthreads();
+}
+
+// dst = a + s * b, elementwise over n floats
+__device__ void tok_axpy(float* dst, const float* a, const float* b, float s, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = a[i] + s * b[i];
+    __syncthreads();
+}
+
+// softmax(q k^T / sqrt(hd)) v for a handful of tokens, all in shared memory; one thread per (head, query)
+__device__ void tok_small_attention(const float* q, const float* k, const float* v, int ld, int nq, int nk, int hd,
+                                    float* out) {
+    const float scale = rsqrtf(static_cast<float>(hd));
+    for (int idx = threadIdx.x; idx < NH * nq; idx += blockDim.x) {
+        const int h = idx / nq, i = idx % nq;
+        float lg[MAXC], mx = -INFINITY;
+        for (int j = 0; j < nk; ++j) {
+            float s = 0.f;
+            for (int d = 0; d < hd; ++d) s = fmaf(q[i * ld + h * hd + d], k[j * ld + h * hd + d], s);
+            lg[j] = s * scale;
+            mx = fmaxf(mx, lg[j]);
+        }
+        float l = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            lg[j] = expf(lg[j] - mx);
+            l += lg[j];
+        }
+        const float inv = 1.f / l;
+        for (int d = 0; d < hd; ++d) {
+            float a = 0.f;
+            for (int j = 0; j < nk; ++j) a = fmaf(lg[j], v[j * ld + h * hd + d], a);
+            out[i * ld + h * hd + d] = a * inv;
+        }
+    }
+    __syncthreads();
+}
+
+// Token -> image attention: 6 queries (smem, [6][128]) against the T keys of this image (fp32 [T,128] in HBM).
+// Warp = (head, half of the tokens); each lane walks keys lane, lane+32, ... with an online softmax, the 32 partial
+// states are merged at the end.
+__device__ void tok_image_attention(const float* qs, const float* __restrict__ kimg, const float* __restrict__ vimg,
+                                    int T, float* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = warp & 7, g = warp >> 3;       // TOK_THREADS = 512: 16 warps
+    float m[3], l[3], acc[3][16];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        m[t] = -INFINITY;
+        l[t] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
+    }
+    for (int key = lane; key < T; key += 32) {
+        float kf[16], vf[16];
+        const float4* kp = reinterpret_cast<const float4*>(kimg + static_cast<long long>(key) * DI + h * 16);
+        const float4* vp = reinterpret_cast<const float4*>(vimg + static_cast<long long>(key) * DI + h * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a = __ldg(kp + i), c = __ldg(vp + i);
+            kf[4 * i] = a.x; kf[4 * i + 1] = a.y; kf[4 * i + 2] = a.z; kf[4 * i + 3] = a.w;
+            vf[4 * i] = c.x; vf[4 * i + 1] = c.y; vf[4 * i + 2] = c.z; vf[4 * i + 3] = c.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            float s = 0.f;
+            const float4* qp = reinterpret_cast<const float4*>(qs + (3 * g + t) * DI + h * 16);     // warp-uniform: broadcast
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 qq = qp[i];
+                s = fmaf(qq.x, kf[4 * i], s);
+                s = fmaf(qq.y, kf[4 * i + 1], s);
+                s = fmaf(qq.z, kf[4 * i + 2], s);
+                s = fmaf(qq.w, kf[4 * i + 3], s);
+            }
+            s *= 0.25f;      // 1 / sqrt(16)
+            if (s > m[t]) {
+                const float c = expf(m[t] - s);
+                l[t] *= c;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) acc[t][d] *= c;
+                m[t] = s;
+            }
+            const float p = expf(s - m[t]);
+            l[t] += p;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[t][d] = fmaf(p, vf[d], acc[t][d]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const float mm = warp_max(m[t]);
+        const float c = (m[t] == -INFINITY) ? 0.f : expf(m[t] - mm);
+        const float lt = warp_sum(l[t] * c);
+        const float inv = 1.f / lt;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const float a = warp_sum(acc[t][d] * c);
+            if (lane == 0) out[(3 * g + t) * DI + h * 16 + d] = a * inv;
+        }
+    }
+    __syncthreads();
+}
+
+// Shared-memory plan of the token kernels (floats)
+constexpr int SM_Q = 0;                       // queries          [6][256]
+constexpr int SM_PE = SM_Q + NTOK * DD;       // query_pe         [6][256]
+constexpr int SM_X = SM_PE + NTOK * DD;       // queries (+ pe)   [6][256]
+constexpr int SM_T1 = SM_X + NTOK * DD;       // scratch          [8][256] each
+constexpr int SM_T2 = SM_T1 + MAXC * DD;
+constexpr int SM_T3 = SM_T2 + MAXC * DD;
+constexpr int SM_T4 = SM_T3 + MAXC * DD;
+constexpr int SM_CND = SM_T4 + MAXC * DD;     // prompt tokens    [8][256]
+constexpr int SM_CN2 = SM_CND + MAXC * DD;    // 2 * prompt       [8][256]  (k = cond + cond, transformer_maskdecoder_edge.py:188)
+constexpr int SM_HID = SM_CN2 + MAXC * DD;    // MLP hidden       [6][mlp_dim]
+
+// One TwoWayAttentionBlock, token side (transformer_maskdecoder_edge.py:161-199), for image blockIdx.x; then the key /
+// value projections that the image side of the same block consumes (:201-212).
+__global__ void __launch_bounds__(TOK_THREADS) dec_token_layer_kernel(
+    LayerW w, int first, int nc, int T, float eps, const float* __restrict__ tokens0, const float* __restrict__ cond,
+    float* __restrict__ qbuf, const float* __restrict__ kimg, const float* __restrict__ vimg, float* __restrict__ kc,
+    float* __restrict__ vc, float* __restrict__ ktok, float* __restrict__ vtok) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x;
+    float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3,
+          *T4 = sm + SM_T4, *CND = sm + SM_CND, *CN2 = sm + SM_CN2, *HID = sm + SM_HID;
+    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
+        PE[i] = tokens0[i];
+        Q[i] = first ? tokens0[i] : qbuf[static_cast<long long>(b) * NTOK * DD + i];
+    }
+    for (int i = threadIdx.x; i < nc * DD; i += blockDim.x) {
+        const float c = cond[static_cast<long long>(b) * nc * DD + i];
+        CND[i] = c;
+        CN2[i] = c + c;
+    }
+    __syncthreads();
+    // ---- self attention (:163-170); the first layer skips the positional term and the shortcut
+    tok_axpy(X, Q, PE, first ? 0.f : 1.f, NTOK * DD);
+    tok_linear<NTOK>(w.self_attn.qw, w.self_attn.qb, X, DD, DD, T1, DD, DD, false);
+    tok_linear<NTOK>(w.self_attn.kw, w.self_attn.kb, X, DD, DD, T2, DD, DD, false);
+    tok_linear<NTOK>(w.self_attn.vw, w.self_attn.vb, Q, DD, DD, T3, DD, DD, false);
+    tok_small_attention(T1, T2, T3, DD, NTOK, NTOK, DD / NH, T4);
+    tok_linear<NTOK>(w.self_attn.ow, w.self_attn.ob, T4, DD, DD, T1, DD, DD, false);
+    tok_add_ln(Q, T1, first ? nullptr : Q, w.n1, eps, NTOK);
+    // ---- token -> image cross attention (:172-177); kimg = (keys + pe) Wk, vimg = keys Wv come from the GEMMs
+    tok_axpy(X, Q, PE, 1.f, NTOK * DD);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false);
+    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false);
+    tok_add_ln(Q, Q, T1, w.n2, eps, NTOK);
+    // ---- token -> prompt cross attention (:179-192): q = queries + pe, k = cond + cond, v = cond
+    tok_axpy(X, Q, PE, 1.f, NTOK * DD);
+    tok_linear<NTOK>(w.t2c.qw, w.t2c.qb, X, DD, DD, T1, DI, DI, false);
+    tok_linear<MAXC>(w.t2c.kw, w.t2c.kb, CN2, DD, DD, T2, DI, DI, false);
+    tok_linear<MAXC>(w.t2c.vw, w.t2c.vb, CND, DD, DD, T3, DI, DI, false);
+    tok_small_attention(T1, T2, T3, DI, NTOK, nc, DI / NH, T4);
+    tok_linear<NTOK>(w.t2c.ow, w.t2c.ob, T4, DI, DI, T1, DD, DD, false);
+    tok_add_ln(Q, Q, T1, w.n2c, eps, NTOK);
+    // ---- MLP (:194-197), ReLU
+    tok_linear<NTOK>(w.l1w, w.l1b, Q, DD, DD, HID, w.mlp_dim, w.mlp_dim, true);
+    tok_linear<NTOK>(w.l2w, w.l2b, HID, w.mlp_dim, w.mlp_dim, T1, DD, DD, false);
+    tok_add_ln(Q, Q, T1, w.n3, eps, NTOK);
+    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) qbuf[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
+    // ---- keys / values of the two image-side attentions of this block (:201-212)
+    tok_linear<MAXC>(w.i2c.kw, w.i2c.kb, CN2, DD, DD, T1, DI, DI, false);
+    tok_linear<MAXC>(w.i2c.vw, w.i2c.vb, CND, DD, DD, T2, DI, DI, false);
+    tok_axpy(X, Q, PE, 1.f, NTOK * DD);
+    tok_linear<NTOK>(w.i2t.kw, w.i2t.kb, X, DD, DD, T3, DI, DI, false);
+    tok_linear<NTOK>(w.i2t.vw, w.i2t.vb, Q, DD, DD, T4, DI, DI, false);
+    for (int i = threadIdx.x; i < nc * DI; i += blockDim.x) {
+        kc[static_cast<long long>(b) * nc * DI + i] = T1[i];
+        vc[static_cast<long long>(b) * nc * DI + i] = T2[i];
+    }
+    for (int i = threadIdx.x; i < NTOK * DI; i += blockDim.x) {
+        ktok[static_cast<long long>(b) * NTOK * DI + i] = T3[i];
+        vtok[static_cast<long long>(b) * NTOK * DI + i] = T4[i];
+    }
+}
+
+__device__ void tok_mlp3(const Mlp3W& w, const float* x, int out_dim, float* t1, float* t2, float* y) {
+    tok_linear<1>(w.w0, w.b0, x, DD, DD, t1, DD, DD, true);
+    tok_linear<1>(w.w1, w.b1, t1, DD, DD, t2, DD, DD, true);
+    tok_linear<1>(w.w2, w.b2, t2, DD, DD, y, out_dim, out_dim, false);
+}
+
+// final_attn_token_to_image + norm_final_attn (transformer_maskdecoder_edge.py:98-109), then the hyper-network MLPs,
+// the edge MLP and the IoU head (mask_decoder_edge.py:160-186).  hyper fp32 [B,5,32], iou fp32 [B,4], hs fp32 [B,6,256].
+__global__ void __launch_bounds__(TOK_THREADS) dec_token_final_kernel(FinalW w, int T, float eps,
+                                                                      const float* __restrict__ tokens0,
+                                                                      const float* __restrict__ qbuf,
+                                                                      const float* __restrict__ kimg,
+                                                                      const float* __restrict__ vimg,
+                                                                      float* __restrict__ hs, float* __restrict__ hyper,
+                                                                      float* __restrict__ iou) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x;
+    float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3;
+    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
+        PE[i] = tokens0[i];
+        Q[i] = qbuf[static_cast<long long>(b) * NTOK * DD + i];
+    }
+    __syncthreads();
+    tok_axpy(X, Q, PE, 1.f, NTOK * DD);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false);
+    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false);
+    tok_add_ln(Q, Q, T1, w.nf, eps, NTOK);
+    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) hs[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
+    for (int i = 0; i <= NMASK; ++i)
+        tok_mlp3(w.hyper[i], Q + (1 + i) * DD, DE, T1, T2, T3 + i * DE);
+    tok_mlp3(w.iou, Q, NMASK, T1, T2, T3 + (NMASK + 1) * DE);
+    for (int i = threadIdx.x; i < (NMASK + 1) * DE; i += blockDim.x) hyper[static_cast<long long>(b) * (NMASK + 1) * DE + i] = T3[i];
+    for (int i = threadIdx.x; i < NMASK; i += blockDim.x) iou[b * NMASK + i] = T3[(NMASK + 1) * DE + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 3x3 im2col over a map stored in nested pixel order (see the header): rows stay in nested order, column
+// (ty*3+tx)*C + c holds channel c of pixel (Y+ty-1, X+tx-1) or zero outside the map; columns >= 9C are zero padding.
+// One thread per (pixel, tap).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nested_to_raster(int n, int g, int& Y, int& X) {
+    const int p = n >> 4, s1 = (n >> 2) & 3, s2 = n & 3;
+    Y = (p / g) * 4 + (s1 >> 1) * 2 + (s2 >> 1);
+    X = (p % g) * 4 + (s1 & 1) * 2 + (s2 & 1);
+}
+__device__ __forceinline__ int raster_to_nested(int Y, int X, int g) {
+    return ((((Y >> 2) * g + (X >> 2)) * 4 + ((Y >> 1) & 1) * 2 + ((X >> 1) & 1)) << 2) + (Y & 1) * 2 + (X & 1);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) dec_im2col3_nested_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 __nv_bfloat16* __restrict__ col, int g, int taps,
+                                                                 int ldcol, long long total) {
+    const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int tap = static_cast<int>(idx % taps);
+    const long long row = idx / taps;
+    const int P2 = 16 * g * g, S = 4 * g;
+    const int n = static_cast<int>(row % P2);
+    const long long img = row / P2;
+    uint4* dst = reinterpret_cast<uint4*>(col + row * ldcol + tap * C);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* src = nullptr;
+    if (tap < 9) {
+        int Y, X;
+        nested_to_raster(n, g, Y, X);
+        const int yy = Y + tap / 3 - 1, xx = X + tap % 3 - 1;
+        if (yy >= 0 && yy < S && xx >= 0 && xx < S)
+            src = reinterpret_cast<const uint4*>(x + (img * P2 + raster_to_nested(yy, xx, g)) * C);
+    }
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i) dst[i] = src ? src[i] : zero;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// masks = hyper[:4] . upscaled, edge = sigmoid(hyper[4] . edge_embedding), masks = masks * edge + masks
+// (mask_decoder_edge.py:176-183).  One thread per output pixel in raster order; inputs in nested order.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_masks_kernel(const float* __restrict__ up, const float* __restrict__ ee,
+                                                        const float* __restrict__ hyper, float* __restrict__ masks,
+                                                        float* __restrict__ edge, int g) {
+    __shared__ float hy[(NMASK + 1) * DE];
+    const int b = blockIdx.y, S = 4 * g, P2 = S * S;
+    if (threadIdx.x < (NMASK + 1) * DE) hy[threadIdx.x] = hyper[b * (NMASK + 1) * DE + threadIdx.x];
+    __syncthreads();
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= P2) return;
+    const int Y = pix / S, X = pix % S;
+    const long long row = static_cast<long long>(b) * P2 + raster_to_nested(Y, X, g);
+    float u[DE], e[DE];
+    const float4* upp = reinterpret_cast<const float4*>(up + row * DE);
+    const float4* eep = reinterpret_cast<const float4*>(ee + row * DE);
+#pragma unroll
+    for (int i = 0; i < DE / 4; ++i) {
+        const float4 a = upp[i], c = eep[i];
+        u[4 * i] = a.x; u[4 * i + 1] = a.y; u[4 * i + 2] = a.z; u[4 * i + 3] = a.w;
+        e[4 * i] = c.x; e[4 * i + 1] = c.y; e[4 * i + 2] = c.z; e[4 * i + 3] = c.w;
+    }
+    float ed = 0.f;
+#pragma unroll
+    for (int d = 0; d < DE; ++d) ed = fmaf(hy[NMASK * DE + d], e[d], ed);
+    ed = 1.f / (1.f + expf(-ed));
+    edge[static_cast<long long>(b) * P2 + pix] = ed;
+#pragma unroll
+    for (int i = 0; i < NMASK; ++i) {
+        float m = 0.f;
+#pragma unroll
+        for (int d = 0; d < DE; ++d) m = fmaf(hy[i * DE + d], u[d], m);
+        masks[(static_cast<long long>(b) * NMASK + i) * P2 + pix] = __fadd_rn(__fmul_rn(m, ed), m);
+    }
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) on fp32 NCHW planes (postprocess_masks,
+// models/sam_maskdecoder_edge.py:380-387)
+__global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              int ih, int iw, int oh, int ow, float sh, float sw,
+                                                              long long total) {
+    const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = static_cast<int>(idx % ow), oy = static_cast<int>((idx / ow) % oh);
+    const long long plane = idx / (static_cast<long long>(ow) * oh);
+    const float fy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(fy), ih - 1), x0 = min(static_cast<int>(fx), iw - 1);
+    const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = in + plane * ih * iw;
+    out[idx] = hy * (hx * p[y0 * iw + x0] + lx * p[y0 * iw + x1]) + ly * (hx * p[y1 * iw + x0] + lx * p[y1 * iw + x1]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+struct DecWorkspace {
+    long long keys, kb, kpb, eb, pos, kimg, vimg, qi, ao, u1, h1, up, upb, ef, col, m1, mh, ee, qbuf, kc, vc, ktok, vtok,
+        hyper, hs, total;
+};
+
+DecWorkspace plan(const cvlm_decoder_config& c, int batch) {
+    const long long T = static_cast<long long>(c.grid) * c.grid, M = T * batch, P1 = 4 * M, P2 = 16 * M;
+    DecWorkspace w;
+    long long off = 0;
+    auto take = [&](long long bytes) {
+        const long long o = off;
+        off = align_up(off + bytes, 1024);
+        return o;
+    };
+    w.keys = take(M * DD * 4);
+    w.kb = take(M * DD * 2);
+    w.kpb = take(M * DD * 2);
+    w.eb = take(M * DD * 2);
+    w.pos = take(T * DD * 4);
+    w.kimg = take(M * DI * 4);
+    w.vimg = take(M * DI * 4);
+    w.qi = take(M * DI * 4);
+    w.ao = take(M * DI * 2);
+    w.u1 = take(M * DD * 4);
+    w.h1 = take(P1 * DQ * 2);
+    w.up = take(P2 * DE * 4);
+    w.upb = take(P2 * DE * 2);
+    w.ef = take(P2 * DE * 4);
+    w.col = take(P2 * 9 * DQ * 2);
+    w.m1 = take(P2 * DQ * 4);
+    w.mh = take(P2 * DQ * 2);
+    w.ee = take(P2 * DE * 4);
+    w.qbuf = take(static_cast<long long>(batch) * NTOK * DD * 4);
+    w.kc = take(static_cast<long long>(batch) * MAXC * DI * 4);
+    w.vc = take(static_cast<long long>(batch) * MAXC * DI * 4);
+    w.ktok = take(static_cast<long long>(batch) * NTOK * DI * 4);
+    w.vtok = take(static_cast<long long>(batch) * NTOK * DI * 4);
+    w.hyper = take(static_cast<long long>(batch) * (NMASK + 1) * DE * 4);
+    w.hs = take(static_cast<long long>(batch) * NTOK * DD * 4);
+    w.total = off;
+    return w;
+}
+
+int check_config(const cvlm_decoder_config& c) {
+    if (c.dim != DD || c.heads != NH || c.num_mask_tokens != NMASK)
+        return set_error(CVLM_ERR_UNSUPPORTED, "decoder: transformer_dim %d / heads %d / mask tokens %d (kernels are built for 256 / 8 / 4)",
+                         c.dim, c.heads, c.num_mask_tokens);
+    if (c.depth < 1 || c.depth > 8) return set_error(CVLM_ERR_UNSUPPORTED, "decoder: depth %d outside [1, 8]", c.depth);
+    if (c.mlp_dim < 128 || c.mlp_dim % 128 || c.mlp_dim > 4096)
+        return set_error(CVLM_ERR_UNSUPPORTED, "decoder: mlp_dim %d must be a multiple of 128 up to 4096", c.mlp_dim);
+    if (c.grid < 8 || c.grid % 8 || c.grid > 128)
+        return set_error(CVLM_ERR_UNSUPPORTED, "decoder: embedding side %d must be a multiple of 8 in [8, 128]", c.grid);
+    if (c.cond_tokens < 1 || c.cond_tokens > MAXC)
+        return set_error(CVLM_ERR_UNSUPPORTED, "decoder: %d prompt tokens per image outside [1, %d]", c.cond_tokens, MAXC);
+    return CVLM_OK;
+}
+
+struct DecFwd {
+    cvlm_decoder* dec;
+    cudaStream_t stream;
+    long long launches = 0;
+    char name[160];
+
+    int get(const char* nm, long long bytes, const void** out) {
+        auto it = dec->tensors.find(nm);
+        if (it == dec->tensors.end()) return set_error(CVLM_ERR_MISSING, "decoder tensor '%s' was not registered", nm);
+        if (bytes > 0 && it->second.second != bytes)
+            return set_error(CVLM_ERR_MISSING, "decoder tensor '%s' has %lld bytes, expected %lld", nm, it->second.second, bytes);
+        *out = it->second.first;
+        return CVLM_OK;
+    }
+    int getf(const char* prefix, const char* suffix, long long elems, const float** out) {
+        snprintf(name, sizeof(name), "%s%s", prefix, suffix);
+        const void* p = nullptr;
+        CVLM_TRY(get(name, elems * 4, &p));
+        *out = static_cast<const float*>(p);
+        return CVLM_OK;
+    }
+    int geth(const char* prefix, const char* suffix, long long elems, const void** out) {
+        snprintf(name, sizeof(name), "%s%s", prefix, suffix);
+        return get(name, elems * 2, out);
+    }
+    int attn(const char* prefix, int inner, AttnW* a) {
+        char p[128];
+        snprintf(p, sizeof(p), "%s", prefix);
+        CVLM_TRY(getf(p, ".q_proj.weight", static_cast<long long>(inner) * DD, &a->qw));
+        CVLM_TRY(getf(p, ".q_proj.bias", inner, &a->qb));
+        CVLM_TRY(getf(p, ".k_proj.weight", static_cast<long long>(inner) * DD, &a->kw));
+        CVLM_TRY(getf(p, ".k_proj.bias", inner, &a->kb));
+        CVLM_TRY(getf(p, ".v_proj.weight", static_cast<long long>(inner) * DD, &a->vw));
+        CVLM_TRY(getf(p, ".v_proj.bias", inner, &a->vb));
+        CVLM_TRY(getf(p, ".out_proj.weight", static_cast<long long>(inner) * DD, &a->ow));
+        CVLM_TRY(getf(p, ".out_proj.bias", DD, &a->ob));
+        return CVLM_OK;
+    }
+    int norm(const char* prefix, int c, NormW* n) {
+        char p[128];
+        snprintf(p, sizeof(p), "%s", prefix);
+        CVLM_TRY(getf(p, ".weight", c, &n->w));
+        CVLM_TRY(getf(p, ".bias", c, &n->b));
+        return CVLM_OK;
+    }
+    int mlp3(const char* prefix, int hidden, int out, Mlp3W* m) {
+        char p[128];
+        snprintf(p, sizeof(p), "%s", prefix);
+        CVLM_TRY(getf(p, ".layers.0.weight", static_cast<long long>(hidden) * DD, &m->w0));
+        CVLM_TRY(getf(p, ".layers.0.bias", hidden, &m->b0));
+        CVLM_TRY(getf(p, ".layers.1.weight", static_cast<long long>(hidden) * hidden, &m->w1));
+        CVLM_TRY(getf(p, ".layers.1.bias", hidden, &m->b1));
+        CVLM_TRY(getf(p, ".layers.2.weight", static_cast<long long>(out) * hidden, &m->w2));
+        CVLM_TRY(getf(p, ".layers.2.bias", out, &m->b2));
+        return CVLM_OK;
+    }
+    // out[M, n] = a[M, k] * w[n, k]^T + bias (+ residual), fp32 output unless out_bf16; optional GELU / bf16 copy
+    int gemm(const void* a, long long m, int k, const void* w, int n, const float* bias, const float* residual, void* out,
+             int gelu = 0, void* copy = nullptr) {
+        GemmArgs g;
+        g.a1 = a; g.lda1 = k; g.b1 = w; g.ldb1 = k; g.k1 = k;
+        g.m = static_cast<int>(m); g.n = n;
+        g.bias = bias; g.residual = residual; g.ldr = n;
+        g.out = out; g.ldo = n; g.out_bf16 = 0; g.act_gelu = gelu;
+        g.copy_bf16 = copy; g.ldc = n;
+        ++launches;
+        return gemm_launch(g, stream);
+    }
+};
+
+template <int C>
+int ln_rows(DecFwd& f, const float* x, const float* gamma, const float* beta, float eps, int gelu, const float* pos, int T,
+            float* out_f32, void* out_b16, void* out_pos_b16, long long rows) {
+    ++f.launches;
+    dec_ln_rows_kernel<C><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, f.stream>>>(
+        x, gamma, beta, eps, gelu, pos, T, out_f32, static_cast<__nv_bfloat16*>(out_b16),
+        static_cast<__nv_bfloat16*>(out_pos_b16), rows);
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
+int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, const float* sparse, const float* dense,
+                    int dense_batch, int batch, float* masks, float* edge, float* iou, float* hs_out, void* workspace,
+                    long long workspace_bytes, cudaStream_t stream) {
+    const cvlm_decoder_config& c = dec->cfg;
+    if (!emb || !image_pe || !sparse || !dense || !masks || !edge || !iou || !workspace)
+        return set_error(CVLM_ERR_ARG, "decoder_forward: null pointer");
+    if (batch < 1) return set_error(CVLM_ERR_ARG, "decoder_forward: batch %d", batch);
+    if (dense_batch != 1 && dense_batch != batch)
+        return set_error(CVLM_ERR_ARG, "decoder_forward: dense prompt batch %d must be 1 or %d", dense_batch, batch);
+    const DecWorkspace ws = plan(c, batch);
+    if (workspace_bytes < ws.total)
+        return set_error(CVLM_ERR_WORKSPACE, "decoder_forward: workspace %lld < %lld bytes", workspace_bytes, ws.total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(CVLM_ERR_ARG, "decoder_forward: workspace must be 1 KiB aligned");
+    const int g = c.grid, T = g * g, nc = c.cond_tokens;
+    const long long M = static_cast<long long>(T) * batch, P1 = 4 * M, P2 = 16 * M;
+    if (P2 * 9 >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
+    char* base = static_cast<char*>(workspace);
+    auto F32 = [&](long long off) { return reinterpret_cast<float*>(base + off); };
+    auto PTR = [&](long long off) { return static_cast<void*>(base + off); };
+    DecFwd f{dec, stream};
+    const size_t tok_smem = static_cast<size_t>(SM_HID + NTOK * c.mlp_dim) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CVLM_CUDA(cudaFuncSetAttribute(dec_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CVLM_CUDA(cudaFuncSetAttribute(dec_token_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (tok_smem > 200 * 1024) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: mlp_dim %d needs too much shared memory", c.mlp_dim);
+
+    // tokens: [iou_token; mask_tokens; edge_token] (mask_decoder_edge.py:157), packed by the host side
+    const float* tokens0 = nullptr;
+    CVLM_TRY(f.getf("tokens", "", NTOK * DD, &tokens0));
+
+    // ---- layout + prompt add
+    ++f.launches;
+    dec_prep_kernel<<<dim3(T / 32, batch), 256, 0, stream>>>(
+        emb, dense, dense_batch == 1 ? 0 : static_cast<long long>(DD) * T, image_pe, F32(ws.keys),
+        static_cast<__nv_bfloat16*>(PTR(ws.kb)), static_cast<__nv_bfloat16*>(PTR(ws.kpb)),
+        static_cast<__nv_bfloat16*>(PTR(ws.eb)), F32(ws.pos), T);
+    CVLM_CUDA(cudaGetLastError());
+
+    // ---- embedding_encoder(image_embeddings) (mask_decoder_edge.py:124, :82-87): edge features, nested order
+    {
+        const void *w0, *w3;
+        const float *b0, *b3, *lw, *lb;
+        CVLM_TRY(f.geth("embedding_encoder.0", ".wp", 4ll * DQ * DD, &w0));
+        CVLM_TRY(f.getf("embedding_encoder.0", ".bp", 4 * DQ, &b0));
+        CVLM_TRY(f.getf("embedding_encoder.1", ".weight", DQ, &lw));
+        CVLM_TRY(f.getf("embedding_encoder.1", ".bias", DQ, &lb));
+        CVLM_TRY(f.geth("embedding_encoder.3", ".wp", 4ll * DE * DQ, &w3));
+        CVLM_TRY(f.getf("embedding_encoder.3", ".bp", 4 * DE, &b3));
+        CVLM_TRY(f.gemm(PTR(ws.eb), M, DD, w0, 4 * DQ, b0, nullptr, PTR(ws.u1)));
+        CVLM_TRY(ln_rows<DQ>(f, F32(ws.u1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.h1), nullptr, P1));
+        CVLM_TRY(f.gemm(PTR(ws.h1), P1, DQ, w3, 4 * DE, b3, nullptr, PTR(ws.ef)));
+    }
+
+    // ---- TwoWayTransformer
+    char pre[128], sub[160];
+    for (int i = 0; i < c.depth; ++i) {
+        snprintf(pre, sizeof(pre), "transformer.layers.%d", i);
+        LayerW lw;
+        lw.mlp_dim = c.mlp_dim;
+        snprintf(sub, sizeof(sub), "%s.self_attn", pre);                  CVLM_TRY(f.attn(sub, DD, &lw.self_attn));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_token_to_image", pre);  CVLM_TRY(f.attn(sub, DI, &lw.t2i));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_token_to_cond", pre);   CVLM_TRY(f.attn(sub, DI, &lw.t2c));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_image_to_token", pre);  CVLM_TRY(f.attn(sub, DI, &lw.i2t));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_image_to_cond", pre);   CVLM_TRY(f.attn(sub, DI, &lw.i2c));
+        snprintf(sub, sizeof(sub), "%s.norm1", pre);                      CVLM_TRY(f.norm(sub, DD, &lw.n1));
+        snprintf(sub, sizeof(sub), "%s.norm2", pre);                      CVLM_TRY(f.norm(sub, DD, &lw.n2));
+        snprintf(sub, sizeof(sub), "%s.norm2_cond", pre);                 CVLM_TRY(f.norm(sub, DD, &lw.n2c));
+        snprintf(sub, sizeof(sub), "%s.norm3", pre);                      CVLM_TRY(f.norm(sub, DD, &lw.n3));
+        NormW n4, n4c;
+        snprintf(sub, sizeof(sub), "%s.norm4", pre);                      CVLM_TRY(f.norm(sub, DD, &n4));
+        snprintf(sub, sizeof(sub), "%s.norm4_cond", pre);                 CVLM_TRY(f.norm(sub, DD, &n4c));
+        snprintf(sub, sizeof(sub), "%s.mlp.lin1", pre);
+        CVLM_TRY(f.getf(sub, ".weight", static_cast<long long>(c.mlp_dim) * DD, &lw.l1w));
+        CVLM_TRY(f.getf(sub, ".bias", c.mlp_dim, &lw.l1b));
+        snprintf(sub, sizeof(sub), "%s.mlp.lin2", pre);
+        CVLM_TRY(f.getf(sub, ".weight", static_cast<long long>(c.mlp_dim) * DD, &lw.l2w));
+        CVLM_TRY(f.getf(sub, ".bias", DD, &lw.l2b));
+        const void *wk, *wv, *wqc, *woc, *wqt, *wot;
+        snprintf(sub, sizeof(sub), "%s.cross_attn_token_to_image", pre);
+        CVLM_TRY(f.geth(sub, ".k_proj.weight.bf16", static_cast<long long>(DI) * DD, &wk));
+        CVLM_TRY(f.geth(sub, ".v_proj.weight.bf16", static_cast<long long>(DI) * DD, &wv));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_image_to_cond", pre);
+        CVLM_TRY(f.geth(sub, ".q_proj.weight.bf16", static_cast<long long>(DI) * DD, &wqc));
+        CVLM_TRY(f.geth(sub, ".out_proj.weight.bf16", static_cast<long long>(DI) * DD, &woc));
+        snprintf(sub, sizeof(sub), "%s.cross_attn_image_to_token", pre);
+        CVLM_TRY(f.geth(sub, ".q_proj.weight.bf16", static_cast<long long>(DI) * DD, &wqt));
+        CVLM_TRY(f.geth(sub, ".out_proj.weight.bf16", static_cast<long long>(DI) * DD, &wot));
+
+        // token side needs k = (keys + pe) Wk, v = keys Wv of the CURRENT keys
+        CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wk, DI, lw.t2i.kb, nullptr, PTR(ws.kimg)));
+        CVLM_TRY(f.gemm(PTR(ws.kb), M, DD, wv, DI, lw.t2i.vb, nullptr, PTR(ws.vimg)));
+        ++f.launches;
+        dec_token_layer_kernel<<<batch, TOK_THREADS, tok_smem, stream>>>(lw, i == 0 ? 1 : 0, nc, T, c.ln_eps, tokens0, sparse,
+                                                                          F32(ws.qbuf), F32(ws.kimg), F32(ws.vimg), F32(ws.kc),
+                                                                          F32(ws.vc), F32(ws.ktok), F32(ws.vtok));
+        CVLM_CUDA(cudaGetLastError());
+        // image -> prompt attention, norm4_cond (:201-206)
+        CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wqc, DI, lw.i2c.qb, nullptr, PTR(ws.qi)));
+        ++f.launches;
+        dec_few_key_attn_kernel<<<static_cast<unsigned>(M / 32), 256, 0, stream>>>(F32(ws.qi), F32(ws.kc), F32(ws.vc), nc,
+                                                                                   static_cast<__nv_bfloat16*>(PTR(ws.ao)), T);
+        CVLM_CUDA(cudaGetLastError());
+        CVLM_TRY(f.gemm(PTR(ws.ao), M, DI, woc, DD, lw.i2c.ob, F32(ws.keys), PTR(ws.keys)));
+        CVLM_TRY(ln_rows<DD>(f, F32(ws.keys), n4c.w, n4c.b, c.ln_eps, 0, F32(ws.pos), T, F32(ws.keys), PTR(ws.kb), PTR(ws.kpb), M));
+        // image -> token attention, norm4 (:208-212)
+        CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wqt, DI, lw.i2t.qb, nullptr, PTR(ws.qi)));
+        ++f.launches;
+        dec_few_key_attn_kernel<<<static_cast<unsigned>(M / 32), 256, 0, stream>>>(F32(ws.qi), F32(ws.ktok), F32(ws.vtok), NTOK,
+                                                                                   static_cast<__nv_bfloat16*>(PTR(ws.ao)), T);
+        CVLM_CUDA(cudaGetLastError());
+        CVLM_TRY(f.gemm(PTR(ws.ao), M, DI, wot, DD, lw.i2t.ob, F32(ws.keys), PTR(ws.keys)));
+        CVLM_TRY(ln_rows<DD>(f, F32(ws.keys), n4.w, n4.b, c.ln_eps, 0, F32(ws.pos), T, F32(ws.keys), PTR(ws.kb), PTR(ws.kpb), M));
+    }
+    // ---- final token -> image attention, hyper-networks, IoU head
+    {
+        FinalW fw;
+        CVLM_TRY(f.attn("transformer.final_attn_token_to_image", DI, &fw.t2i));
+        CVLM_TRY(f.norm("transformer.norm_final_attn", DD, &fw.nf));
+        for (int i = 0; i < NMASK; ++i) {
+            snprintf(sub, sizeof(sub), "output_hypernetworks_mlps.%d", i);
+            CVLM_TRY(f.mlp3(sub, DD, DE, &fw.hyper[i]));
+        }
+        CVLM_TRY(f.mlp3("edge_mlp", DD, DE, &fw.hyper[NMASK]));
+        CVLM_TRY(f.mlp3("iou_prediction_head", DD, NMASK, &fw.iou));
+        const void *wk, *wv;
+        CVLM_TRY(f.geth("transformer.final_attn_token_to_image", ".k_proj.weight.bf16", static_cast<long long>(DI) * DD, &wk));
+        CVLM_TRY(f.geth("transformer.final_attn_token_to_image", ".v_proj.weight.bf16", static_cast<long long>(DI) * DD, &wv));
+        CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wk, DI, fw.t2i.kb, nullptr, PTR(ws.kimg)));
+        CVLM_TRY(f.gemm(PTR(ws.kb), M, DD, wv, DI, fw.t2i.vb, nullptr, PTR(ws.vimg)));
+        ++f.launches;
+        dec_token_final_kernel<<<batch, TOK_THREADS, tok_smem, stream>>>(fw, T, c.ln_eps, tokens0, F32(ws.qbuf), F32(ws.kimg),
+                                                                          F32(ws.vimg), hs_out ? hs_out : F32(ws.hs),
+                                                                          F32(ws.hyper), iou);
+        CVLM_CUDA(cudaGetLastError());
+    }
+    // ---- output_upscaling(keys) (mask_decoder_edge.py:165-166, :53-59)
+    {
+        const void *w0, *w3;
+        const float *b0, *b3, *lw, *lb;
+        CVLM_TRY(f.geth("output_upscaling.0", ".wp", 4ll * DQ * DD, &w0));
+        CVLM_TRY(f.getf("output_upscaling.0", ".bp", 4 * DQ, &b0));
+        CVLM_TRY(f.getf("output_upscaling.1", ".weight", DQ, &lw));
+        CVLM_TRY(f.getf("output_upscaling.1", ".bias", DQ, &lb));
+        CVLM_TRY(f.geth("output_upscaling.3", ".wp", 4ll * DE * DQ, &w3));
+        CVLM_TRY(f.getf("output_upscaling.3", ".bp", 4 * DE, &b3));
+        CVLM_TRY(f.gemm(PTR(ws.kb), M, DD, w0, 4 * DQ, b0, nullptr, PTR(ws.u1)));
+        CVLM_TRY(ln_rows<DQ>(f, F32(ws.u1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.h1), nullptr, P1));
+        CVLM_TRY(f.gemm(PTR(ws.h1), P1, DQ, w3, 4 * DE, b3, nullptr, PTR(ws.up), 1, PTR(ws.upb)));
+    }
+    // ---- embedding_maskfeature(upscaled) + edge features (:168, :88-93): two 3x3 transposed convolutions (s1 p1)
+    {
+        const void *w0, *w3;
+        const float *b0, *b3, *lw, *lb;
+        const int k0 = 10 * DE;   // 9 taps x 32 channels padded to a multiple of 64
+        CVLM_TRY(f.geth("embedding_maskfeature.0", ".wp", static_cast<long long>(DQ) * k0, &w0));
+        CVLM_TRY(f.getf("embedding_maskfeature.0", ".bias", DQ, &b0));
+        CVLM_TRY(f.getf("embedding_maskfeature.1", ".weight", DQ, &lw));
+        CVLM_TRY(f.getf("embedding_maskfeature.1", ".bias", DQ, &lb));
+        CVLM_TRY(f.geth("embedding_maskfeature.3", ".wp", static_cast<long long>(DE) * 9 * DQ, &w3));
+        CVLM_TRY(f.getf("embedding_maskfeature.3", ".bias", DE, &b3));
+        ++f.launches;
+        dec_im2col3_nested_kernel<DE><<<static_cast<unsigned>((P2 * 10 + 255) / 256), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 10, k0, P2 * 10);
+        CVLM_CUDA(cudaGetLastError());
+        CVLM_TRY(f.gemm(PTR(ws.col), P2, k0, w0, DQ, b0, nullptr, PTR(ws.m1)));
+        CVLM_TRY(ln_rows<DQ>(f, F32(ws.m1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.mh), nullptr, P2));
+        ++f.launches;
+        dec_im2col3_nested_kernel<DQ><<<static_cast<unsigned>((P2 * 9 + 255) / 256), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 9, 9 * DQ, P2 * 9);
+        CVLM_CUDA(cudaGetLastError());
+        CVLM_TRY(f.gemm(PTR(ws.col), P2, 9 * DQ, w3, DE, b3, F32(ws.ef), PTR(ws.ee)));
+    }
+    // ---- masks, edge
+    ++f.launches;
+    dec_masks_kernel<<<dim3((16 * T + 255) / 256, batch), 256, 0, stream>>>(F32(ws.up), F32(ws.ee), F32(ws.hyper), masks, edge, g);
+    CVLM_CUDA(cudaGetLastError());
+    dec->last_launches = f.launches;
+    return CVLM_OK;
+}
+
+}  // namespace
+
+int bilinear_resize_launch(const float* in, float* out, long long planes, int ih, int iw, int oh, int ow, cudaStream_t stream) {
+    if (!in || !out || planes < 1 || ih < 1 || iw < 1 || oh < 1 || ow < 1) return set_error(CVLM_ERR_ARG, "bilinear_resize: bad arguments");
+    const long long total = planes * oh * ow;
+    bilinear_resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        in, out, ih, iw, oh, ow, static_cast<float>(ih) / oh, static_cast<float>(iw) / ow, total);
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
+}  // namespace cvlm
+
+extern "C" {
+
+int cvlm_decoder_create(const cvlm_decoder_config* cfg, cvlm_decoder** out) {
+    if (!cfg || !out) return cvlm::set_error(CVLM_ERR_ARG, "decoder_create: null argument");
+    CVLM_TRY(cvlm::check_config(*cfg));
+    cvlm_decoder* d = new cvlm_decoder();
+    d->cfg = *cfg;
+    *out = d;
+    return CVLM_OK;
+}
+
+int cvlm_decoder_destroy(cvlm_decoder* dec) {
+    delete dec;
+    return CVLM_OK;
+}
+
+int cvlm_decoder_set_tensor(cvlm_decoder* dec, const char* name, const void* dev_ptr, long long nbytes) {
+    if (!dec || !name || !dev_ptr || nbytes <= 0) return cvlm::set_error(CVLM_ERR_ARG, "decoder_set_tensor: bad argument");
+    if (reinterpret_cast<uintptr_t>(dev_ptr) & 15) return cvlm::set_error(CVLM_ERR_ARG, "decoder_set_tensor: '%s' is not 16-byte aligned", name);
+    dec->tensors[name] = {dev_ptr, nbytes};
+    return CVLM_OK;
+}
+
+long long cvlm_decoder_workspace_bytes(const cvlm_decoder* dec, int batch) {
+    if (!dec || batch < 1) return cvlm::set_error(CVLM_ERR_ARG, "decoder_workspace_bytes: bad argument");
+    return cvlm::plan(dec->cfg, batch).total;
+}
+
+long long cvlm_decoder_last_launches(const cvlm_decoder* dec) { return dec ? dec->last_launches : 0; }
+
+int cvlm_decoder_forward(cvlm_decoder* dec, const float* image_embeddings, const float* image_pe, const float* sparse_prompt,
+                         const float* dense_prompt, int dense_batch, int batch, float* masks, float* edge, float* iou_pred,
+                         float* hs, void* workspace, long long workspace_bytes, cvlm_stream_t stream) {
+    if (!dec) return cvlm::set_error(CVLM_ERR_ARG, "decoder_forward: null handle");
+    return cvlm::decoder_forward(dec, image_embeddings, image_pe, sparse_prompt, dense_prompt, dense_batch, batch, masks, edge,
+                                 iou_pred, hs, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_bilinear_resize(const float* in, float* out, long long planes, int in_h, int in_w, int out_h, int out_w,
+                            cvlm_stream_t stream) {
+    return cvlm::bilinear_resize_launch(in, out, planes, in_h, in_w, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

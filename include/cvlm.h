@@ -178,6 +178,50 @@ int cvlm_op_preprocess_u8(const unsigned char* img, int h, int w, float* out, in
 int cvlm_op_adapter_embed(const float* x0, const float* hand, const float* w_t, const float* cst, void* t_out,
                           int batch, int tokens, int dim, int rank, int rank_pad, cvlm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mask decoder: MaskDecoder_Edge.forward / predict_masks
+ * (models/mmseg/models/sam/mask_decoder_edge.py:96-190) over TwoWayTransformer_MaskDecoder_Edge
+ * (transformer_maskdecoder_edge.py:62-214), batched over images (image b is decoded with prompt b; the
+ * reference itself only works at batch 1).  csrc/decoder.cu.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cvlm_decoder_config {
+    int dim;              /* transformer_dim, 256 */
+    int heads;            /* 8 */
+    int mlp_dim;          /* 2048 */
+    int depth;            /* TwoWayTransformer depth, 2 */
+    int num_mask_tokens;  /* num_multimask_outputs + 1 = 4 (the edge token is added on top) */
+    int grid;             /* side of the image embedding (64) */
+    int cond_tokens;      /* prompt tokens per image in sparse_prompt_embeddings (2) */
+    float ln_eps;         /* nn.LayerNorm of the transformer (1e-5) */
+    float ln2d_eps;       /* LayerNorm2d of the up-scaling stacks (common.py:32, 1e-6) */
+} cvlm_decoder_config;
+
+typedef struct cvlm_decoder cvlm_decoder;
+
+int cvlm_decoder_create(const cvlm_decoder_config* cfg, cvlm_decoder** out);
+int cvlm_decoder_destroy(cvlm_decoder* dec);
+/* fp32 parameters under the reference's state_dict names, plus the bf16 / re-laid-out copies listed in
+ * camouflaged_vlm_b200/mask_decoder.py (pack_decoder_weights). */
+int cvlm_decoder_set_tensor(cvlm_decoder* dec, const char* name, const void* dev_ptr, long long nbytes);
+long long cvlm_decoder_workspace_bytes(const cvlm_decoder* dec, int batch);
+long long cvlm_decoder_last_launches(const cvlm_decoder* dec);
+
+/* predict_masks for `batch` images.
+ *   image_embeddings fp32 NCHW [batch, 256, g, g]        image_pe fp32 NCHW [1, 256, g, g]
+ *   sparse_prompt    fp32 [batch, cond_tokens, 256]       dense_prompt fp32 NCHW [dense_batch, 256, g, g], dense_batch 1 or batch
+ *   masks  fp32 [batch, 4, 4g, 4g]  (all mask tokens; the caller slices like mask_decoder_edge.py:133-139)
+ *   edge   fp32 [batch, 1, 4g, 4g]      iou_pred fp32 [batch, 4]
+ *   hs     NULL or fp32 [batch, 6, 256]: the transformer's output tokens
+ *   workspace: device, 1 KiB aligned, >= cvlm_decoder_workspace_bytes(dec, batch) */
+int cvlm_decoder_forward(cvlm_decoder* dec, const float* image_embeddings, const float* image_pe, const float* sparse_prompt,
+                         const float* dense_prompt, int dense_batch, int batch, float* masks, float* edge, float* iou_pred,
+                         float* hs, void* workspace, long long workspace_bytes, cvlm_stream_t stream);
+
+/* F.interpolate(mode="bilinear", align_corners=False) on `planes` fp32 images [in_h, in_w] -> [out_h, out_w]
+ * (postprocess_masks, models/sam_maskdecoder_edge.py:359-388). */
+int cvlm_op_bilinear_resize(const float* in, float* out, long long planes, int in_h, int in_w, int out_h, int out_w,
+                            cvlm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,14 @@ def main():
         return masks
 
     emb = torch.randn(1, 256, 16, 16, generator=torch.Generator().manual_seed(0))
-    np.savez_compressed(os.path.join(GOLDEN, "decoder_small.npz"), emb=emb.numpy(), logits=ref_decode(emb).numpy())
+    # every output of the reference's predict_masks (all four mask tokens, edge map, IoU head) for the decoder parity tests
+    dense = dsd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(1, -1, 16, 16)
+    with torch.no_grad():
+        m_all, e_all, iou = dec.predict_masks(image_embeddings=emb, edge_embeddings=dec.embedding_encoder(emb),
+                                              image_pe=mdo.dense_pe(dsd, 16), sparse_prompt_embeddings=dsd["probe.sparse"],
+                                              dense_prompt_embeddings=dense)
+    np.savez_compressed(os.path.join(GOLDEN, "decoder_small.npz"), emb=emb.numpy(), logits=ref_decode(emb).numpy(),
+                        masks_all=m_all.numpy(), edge=e_all.numpy(), iou=iou.numpy())
     if args.full:
         out, interm = run_reference("vit_h", 1)
         # full reference cascade tail on the reference embedding: low-res mask logits [1,1,256,256]

@@ -172,17 +172,18 @@ def dense_pe(sd, size: int) -> Tensor:
 
 
 @torch.no_grad()
-def decode_mask_logits(sd: Dict[str, Tensor], emb: Tensor) -> Tensor:
-    """mask_decoder_edge.py forward/predict_masks with multimask_output=False on ONE image embedding
-    [1,256,g,g] -> low-res mask logits [1,1,4g,4g] (the caller upsamples and thresholds at 0,
-    models/sam_maskdecoder_edge.py:355, 359-388)."""
+def decode_all(sd: Dict[str, Tensor], emb: Tensor, sparse: Tensor = None) -> Dict[str, Tensor]:
+    """mask_decoder_edge.py forward/predict_masks on ONE image embedding [1,256,g,g] with the prompt `sparse` [1,n,256]
+    (default: the probe's).  Returns every output of predict_masks (:140-190): masks [1,4,4g,4g] (all mask tokens, after
+    the edge modulation), edge [1,1,4g,4g], iou [1,4], plus the transformer's output tokens hs [1,6,256]."""
     emb = emb.float().cpu()
+    sparse = sd["probe.sparse"] if sparse is None else sparse.float().cpu()
     g = emb.shape[-1]
     up = lambda pre, x: F.conv_transpose2d(x, sd[pre + ".weight"], sd[pre + ".bias"], stride=2)
     edge_feat = up("embedding_encoder.3", F.gelu(_ln2d(sd, "embedding_encoder.1", up("embedding_encoder.0", emb))))
     tokens = torch.cat([sd["iou_token.weight"], sd["mask_tokens.weight"], sd["edge_token.weight"]], 0)[None]
     src = emb + sd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(1, -1, g, g)
-    hs, keys = _two_way_transformer(sd, src, dense_pe(sd, g), tokens, sd["probe.sparse"])
+    hs, keys = _two_way_transformer(sd, src, dense_pe(sd, g), tokens, sparse)
     mask_tokens_out = hs[:, 1:1 + NUM_MASK_TOKENS + 1, :]
     src2 = keys.transpose(1, 2).view(1, DIM, g, g)
     upscaled = F.gelu(up("output_upscaling.3", F.gelu(_ln2d(sd, "output_upscaling.1", up("output_upscaling.0", src2)))))
@@ -196,7 +197,14 @@ def decode_mask_logits(sd: Dict[str, Tensor], emb: Tensor) -> Tensor:
     masks = (hyper[:, :NUM_MASK_TOKENS] @ upscaled.view(b, c, h * w)).view(b, -1, h, w)
     edge = torch.sigmoid((hyper[:, NUM_MASK_TOKENS:] @ edge_emb.view(b, c, h * w)).view(b, -1, h, w))
     masks = masks * edge + masks
-    return masks[:, 0:1]
+    return {"masks": masks, "edge": edge, "iou": _mlp3(sd, "iou_prediction_head", hs[:, 0]), "hs": hs,
+            "keys": keys, "upscaled": upscaled, "edge_emb": edge_emb, "hyper": hyper}
+
+
+def decode_mask_logits(sd: Dict[str, Tensor], emb: Tensor) -> Tensor:
+    """multimask_output=False: low-res mask logits [1,1,4g,4g] (the caller upsamples and thresholds at 0,
+    models/sam_maskdecoder_edge.py:355, 359-388)."""
+    return decode_all(sd, emb)["masks"][:, 0:1]
 
 
 def binary_mask(logits: Tensor, out_size: int) -> Tensor:
