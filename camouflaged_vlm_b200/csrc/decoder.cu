@@ -52,11 +52,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // prep: NCHW -> token-major.  keys = emb + dense, kb = bf16(keys), kpb = bf16(keys + pe), eb = bf16(emb), pos_t = pe.
@@ -233,37 +228,91 @@ struct FinalW {
     Mlp3W iou;
 };
 
-// ys[t][o] = act(sum_k xs[t][k] * W[o][k] + b[o]) for t < NT;  `in` is a multiple of 128 floats
+// ys[t][o] = act(sum_k xs[t][k] * W[o][k] + b[o]) for t < NT, with the weight stored TRANSPOSED (Wt[k][o], packed by the
+// host as "<name>.weight.t"): a thread owns four adjacent output columns, so a warp reads 512 contiguous bytes of one
+// weight row per load; the activations are shared-memory broadcasts.  When there are fewer column groups than threads
+// the K range is split over up to 8 thread groups whose partial sums meet in `red` ([8][NT][out] floats at most) and are
+// added in a fixed order (results do not depend on scheduling).  out % 4 == 0, in % 32 == 0.
 template <int NT>
-__device__ void tok_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* xs, int ldx, int in,
-                           float* ys, int ldy, int out, bool relu) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int o = warp; o < out; o += nw) {
-        float acc[NT];
+__device__ void tok_linear(const float* __restrict__ Wt, const float* __restrict__ bias, const float* xs, int ldx, int in,
+                           float* ys, int ldy, int out, bool relu, float* red) {
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    const int cthreads = out / 4;
+    if (cthreads >= nthr) {
+        // wide layer (MLP lin1): every thread walks the whole K range, several passes over the columns
+        for (int c = tid; c < cthreads; c += nthr) {
+            float acc[NT][4];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = 0.f;
-        const float4* wr = reinterpret_cast<const float4*>(W + static_cast<long long>(o) * in);
-        for (int k4 = lane; k4 < in / 4; k4 += 32) {
-            const float4 w = __ldg(wr + k4);
+            for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+            const float4* wp = reinterpret_cast<const float4*>(Wt) + c;
+#pragma unroll 2
+            for (int k = 0; k < in; k += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w[u] = __ldg(wp + static_cast<long long>(k + u) * cthreads);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + k);
+                    acc[t][0] = fmaf(xv.x, w[0].x, acc[t][0]); acc[t][1] = fmaf(xv.x, w[0].y, acc[t][1]);
+                    acc[t][2] = fmaf(xv.x, w[0].z, acc[t][2]); acc[t][3] = fmaf(xv.x, w[0].w, acc[t][3]);
+                    acc[t][0] = fmaf(xv.y, w[1].x, acc[t][0]); acc[t][1] = fmaf(xv.y, w[1].y, acc[t][1]);
+                    acc[t][2] = fmaf(xv.y, w[1].z, acc[t][2]); acc[t][3] = fmaf(xv.y, w[1].w, acc[t][3]);
+                    acc[t][0] = fmaf(xv.z, w[2].x, acc[t][0]); acc[t][1] = fmaf(xv.z, w[2].y, acc[t][1]);
+                    acc[t][2] = fmaf(xv.z, w[2].z, acc[t][2]); acc[t][3] = fmaf(xv.z, w[2].w, acc[t][3]);
+                    acc[t][0] = fmaf(xv.w, w[3].x, acc[t][0]); acc[t][1] = fmaf(xv.w, w[3].y, acc[t][1]);
+                    acc[t][2] = fmaf(xv.w, w[3].z, acc[t][2]); acc[t][3] = fmaf(xv.w, w[3].w, acc[t][3]);
+                }
+            }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bv = *reinterpret_cast<const float4*>(bias + 4 * c);
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + 4 * k4);
-                acc[t] = fmaf(xv.x, w.x, acc[t]);
-                acc[t] = fmaf(xv.y, w.y, acc[t]);
-                acc[t] = fmaf(xv.z, w.z, acc[t]);
-                acc[t] = fmaf(xv.w, w.w, acc[t]);
+                float4 y = make_float4(acc[t][0] + bv.x, acc[t][1] + bv.y, acc[t][2] + bv.z, acc[t][3] + bv.w);
+                if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+                *reinterpret_cast<float4*>(ys + t * ldy + 4 * c) = y;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    int split = nthr / cthreads;
+    if (split > 8) split = 8;
+    while (split > 1 && in % (split * 4)) split >>= 1;
+    const int kchunk = in / split;
+    const int ks = tid / cthreads, c = tid % cthreads;
+    if (ks < split) {
+        float acc[NT][4];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(Wt) + c;
+#pragma unroll 2
+        for (int k = ks * kchunk; k < (ks + 1) * kchunk; k += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = __ldg(wp + static_cast<long long>(k + u) * cthreads);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + k);
+                acc[t][0] = fmaf(xv.x, w[0].x, acc[t][0]); acc[t][1] = fmaf(xv.x, w[0].y, acc[t][1]);
+                acc[t][2] = fmaf(xv.x, w[0].z, acc[t][2]); acc[t][3] = fmaf(xv.x, w[0].w, acc[t][3]);
+                acc[t][0] = fmaf(xv.y, w[1].x, acc[t][0]); acc[t][1] = fmaf(xv.y, w[1].y, acc[t][1]);
+                acc[t][2] = fmaf(xv.y, w[1].z, acc[t][2]); acc[t][3] = fmaf(xv.y, w[1].w, acc[t][3]);
+                acc[t][0] = fmaf(xv.z, w[2].x, acc[t][0]); acc[t][1] = fmaf(xv.z, w[2].y, acc[t][1]);
+                acc[t][2] = fmaf(xv.z, w[2].z, acc[t][2]); acc[t][3] = fmaf(xv.z, w[2].w, acc[t][3]);
+                acc[t][0] = fmaf(xv.w, w[3].x, acc[t][0]); acc[t][1] = fmaf(xv.w, w[3].y, acc[t][1]);
+                acc[t][2] = fmaf(xv.w, w[3].z, acc[t][2]); acc[t][3] = fmaf(xv.w, w[3].w, acc[t][3]);
             }
         }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = warp_sum(acc[t]);
-        if (lane == 0) {
-            const float bv = bias ? bias[o] : 0.f;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const float y = acc[t] + bv;
-                ys[t * ldy + o] = relu ? fmaxf(y, 0.f) : y;
-            }
-        }
+        for (int t = 0; t < NT; ++t)
+            *reinterpret_cast<float4*>(red + (ks * NT + t) * out + 4 * c) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < NT * out; i += nthr) {
+        const int t = i / out, o = i % out;
+        float y = bias ? bias[o] : 0.f;
+        for (int s2 = 0; s2 < split; ++s2) y += red[(s2 * NT + t) * out + o];
+        ys[t * ldy + o] = relu ? fmaxf(y, 0.f) : y;
     }
     __syncthreads();
 }
@@ -331,67 +380,76 @@ __device__ void tok_small_attention(const float* q, const float* k, const float*
 }
 
 // Token -> image attention: 6 queries (smem, [6][128]) against the T keys of this image (fp32 [T,128] in HBM).
-// Warp = (head, half of the tokens); each lane walks keys lane, lane+32, ... with an online softmax, the 32 partial
-// states are merged at the end.
+// A warp reads one whole key row per load (lane = 4 channels, 4 lanes per head: 512 contiguous bytes), the 16-channel
+// dot products are finished with two shuffles, and every lane carries an online-softmax state (m, l, 4 channels of the
+// output) for the 6 tokens of its head.  The 16 warps take interleaved keys; their states are merged through `red`
+// ([16][6][160] floats) in warp order, so the result does not depend on scheduling.
 __device__ void tok_image_attention(const float* qs, const float* __restrict__ kimg, const float* __restrict__ vimg,
-                                    int T, float* out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = warp & 7, g = warp >> 3;       // TOK_THREADS = 512: 16 warps
-    float m[3], l[3], acc[3][16];
+                                    int T, float* out, float* red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float4 q[NTOK], acc[NTOK];
+    float m[NTOK], l[NTOK];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
+    for (int t = 0; t < NTOK; ++t) {
+        q[t] = *reinterpret_cast<const float4*>(qs + t * DI + 4 * lane);
+        q[t].x *= 0.25f; q[t].y *= 0.25f; q[t].z *= 0.25f; q[t].w *= 0.25f;      // 1 / sqrt(16)
+        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
         m[t] = -INFINITY;
         l[t] = 0.f;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[t][d] = 0.f;
     }
-    for (int key = lane; key < T; key += 32) {
-        float kf[16], vf[16];
-        const float4* kp = reinterpret_cast<const float4*>(kimg + static_cast<long long>(key) * DI + h * 16);
-        const float4* vp = reinterpret_cast<const float4*>(vimg + static_cast<long long>(key) * DI + h * 16);
+    const float4* kp = reinterpret_cast<const float4*>(kimg) + lane;
+    const float4* vp = reinterpret_cast<const float4*>(vimg) + lane;
+    for (int key = warp; key < T; key += 2 * nw) {
+        const bool two = key + nw < T;
+        const float4 k0 = __ldg(kp + static_cast<long long>(key) * (DI / 4));
+        const float4 v0 = __ldg(vp + static_cast<long long>(key) * (DI / 4));
+        const float4 k1 = two ? __ldg(kp + static_cast<long long>(key + nw) * (DI / 4)) : k0;
+        const float4 v1 = two ? __ldg(vp + static_cast<long long>(key + nw) * (DI / 4)) : v0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 a = __ldg(kp + i), c = __ldg(vp + i);
-            kf[4 * i] = a.x; kf[4 * i + 1] = a.y; kf[4 * i + 2] = a.z; kf[4 * i + 3] = a.w;
-            vf[4 * i] = c.x; vf[4 * i + 1] = c.y; vf[4 * i + 2] = c.z; vf[4 * i + 3] = c.w;
-        }
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            float s = 0.f;
-            const float4* qp = reinterpret_cast<const float4*>(qs + (3 * g + t) * DI + h * 16);     // warp-uniform: broadcast
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 qq = qp[i];
-                s = fmaf(qq.x, kf[4 * i], s);
-                s = fmaf(qq.y, kf[4 * i + 1], s);
-                s = fmaf(qq.z, kf[4 * i + 2], s);
-                s = fmaf(qq.w, kf[4 * i + 3], s);
-            }
-            s *= 0.25f;      // 1 / sqrt(16)
-            if (s > m[t]) {
-                const float c = expf(m[t] - s);
-                l[t] *= c;
-#pragma unroll
-                for (int d = 0; d < 16; ++d) acc[t][d] *= c;
-                m[t] = s;
-            }
-            const float p = expf(s - m[t]);
-            l[t] += p;
-#pragma unroll
-            for (int d = 0; d < 16; ++d) acc[t][d] = fmaf(p, vf[d], acc[t][d]);
+        for (int t = 0; t < NTOK; ++t) {
+            float s0 = fmaf(q[t].x, k0.x, fmaf(q[t].y, k0.y, fmaf(q[t].z, k0.z, q[t].w * k0.w)));
+            float s1 = fmaf(q[t].x, k1.x, fmaf(q[t].y, k1.y, fmaf(q[t].z, k1.z, q[t].w * k1.w)));
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            if (!two) s1 = -INFINITY;
+            const float mn = fmaxf(m[t], fmaxf(s0, s1));
+            const float c = __expf(m[t] - mn), p0 = __expf(s0 - mn), p1 = __expf(s1 - mn);
+            l[t] = fmaf(l[t], c, p0 + p1);
+            acc[t].x = fmaf(acc[t].x, c, fmaf(p0, v0.x, p1 * v1.x));
+            acc[t].y = fmaf(acc[t].y, c, fmaf(p0, v0.y, p1 * v1.y));
+            acc[t].z = fmaf(acc[t].z, c, fmaf(p0, v0.z, p1 * v1.z));
+            acc[t].w = fmaf(acc[t].w, c, fmaf(p0, v0.w, p1 * v1.w));
+            m[t] = mn;
         }
     }
+    // merge the warps: red[warp][t] = {acc (128 floats), m (32: one per lane), l-less: l is folded below}
+    constexpr int STRIDE = DI + 32 + 32;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const float mm = warp_max(m[t]);
-        const float c = (m[t] == -INFINITY) ? 0.f : expf(m[t] - mm);
-        const float lt = warp_sum(l[t] * c);
+    for (int t = 0; t < NTOK; ++t) {
+        float* r = red + (warp * NTOK + t) * STRIDE;
+        *reinterpret_cast<float4*>(r + 4 * lane) = acc[t];
+        r[DI + lane] = m[t];
+        r[DI + 32 + lane] = l[t];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NTOK * 32; i += blockDim.x) {
+        const int t = i >> 5, ln = i & 31;
+        float mm = -INFINITY;
+        for (int w = 0; w < nw; ++w) mm = fmaxf(mm, red[(w * NTOK + t) * STRIDE + DI + ln]);
+        float lt = 0.f;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < nw; ++w) {
+            const float* r = red + (w * NTOK + t) * STRIDE;
+            const float mw = r[DI + ln];
+            const float c = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
+            lt = fmaf(r[DI + 32 + ln], c, lt);
+            const float4 av = *reinterpret_cast<const float4*>(r + 4 * ln);
+            a.x = fmaf(av.x, c, a.x); a.y = fmaf(av.y, c, a.y); a.z = fmaf(av.z, c, a.z); a.w = fmaf(av.w, c, a.w);
+        }
         const float inv = 1.f / lt;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) {
-            const float a = warp_sum(acc[t][d] * c);
-            if (lane == 0) out[(3 * g + t) * DI + h * 16 + d] = a * inv;
-        }
+        *reinterpret_cast<float4*>(out + t * DI + 4 * ln) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
     }
     __syncthreads();
 }
@@ -406,7 +464,8 @@ constexpr int SM_T3 = SM_T2 + MAXC * DD;
 constexpr int SM_T4 = SM_T3 + MAXC * DD;
 constexpr int SM_CND = SM_T4 + MAXC * DD;     // prompt tokens    [8][256]
 constexpr int SM_CN2 = SM_CND + MAXC * DD;    // 2 * prompt       [8][256]  (k = cond + cond, transformer_maskdecoder_edge.py:188)
-constexpr int SM_HID = SM_CN2 + MAXC * DD;    // MLP hidden       [6][mlp_dim]
+constexpr int SM_RED = SM_CN2 + MAXC * DD;    // split-K partials ([8][6][256] at most) / attention merge [16][6][192]
+constexpr int SM_HID = SM_RED + 16 * NTOK * 192;   // MLP hidden       [6][mlp_dim]
 
 // One TwoWayAttentionBlock, token side (transformer_maskdecoder_edge.py:161-199), for image blockIdx.x; then the key /
 // value projections that the image side of the same block consumes (:201-212).
@@ -417,7 +476,7 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_layer_kernel(
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x;
     float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3,
-          *T4 = sm + SM_T4, *CND = sm + SM_CND, *CN2 = sm + SM_CN2, *HID = sm + SM_HID;
+          *T4 = sm + SM_T4, *CND = sm + SM_CND, *CN2 = sm + SM_CN2, *HID = sm + SM_HID, *RED = sm + SM_RED;
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
         PE[i] = tokens0[i];
         Q[i] = first ? tokens0[i] : qbuf[static_cast<long long>(b) * NTOK * DD + i];
@@ -430,37 +489,37 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_layer_kernel(
     __syncthreads();
     // ---- self attention (:163-170); the first layer skips the positional term and the shortcut
     tok_axpy(X, Q, PE, first ? 0.f : 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.self_attn.qw, w.self_attn.qb, X, DD, DD, T1, DD, DD, false);
-    tok_linear<NTOK>(w.self_attn.kw, w.self_attn.kb, X, DD, DD, T2, DD, DD, false);
-    tok_linear<NTOK>(w.self_attn.vw, w.self_attn.vb, Q, DD, DD, T3, DD, DD, false);
+    tok_linear<NTOK>(w.self_attn.qw, w.self_attn.qb, X, DD, DD, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.self_attn.kw, w.self_attn.kb, X, DD, DD, T2, DD, DD, false, RED);
+    tok_linear<NTOK>(w.self_attn.vw, w.self_attn.vb, Q, DD, DD, T3, DD, DD, false, RED);
     tok_small_attention(T1, T2, T3, DD, NTOK, NTOK, DD / NH, T4);
-    tok_linear<NTOK>(w.self_attn.ow, w.self_attn.ob, T4, DD, DD, T1, DD, DD, false);
+    tok_linear<NTOK>(w.self_attn.ow, w.self_attn.ob, T4, DD, DD, T1, DD, DD, false, RED);
     tok_add_ln(Q, T1, first ? nullptr : Q, w.n1, eps, NTOK);
     // ---- token -> image cross attention (:172-177); kimg = (keys + pe) Wk, vimg = keys Wv come from the GEMMs
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false);
-    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2);
-    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED);
+    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2, RED);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED);
     tok_add_ln(Q, Q, T1, w.n2, eps, NTOK);
     // ---- token -> prompt cross attention (:179-192): q = queries + pe, k = cond + cond, v = cond
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2c.qw, w.t2c.qb, X, DD, DD, T1, DI, DI, false);
-    tok_linear<MAXC>(w.t2c.kw, w.t2c.kb, CN2, DD, DD, T2, DI, DI, false);
-    tok_linear<MAXC>(w.t2c.vw, w.t2c.vb, CND, DD, DD, T3, DI, DI, false);
+    tok_linear<NTOK>(w.t2c.qw, w.t2c.qb, X, DD, DD, T1, DI, DI, false, RED);
+    tok_linear<MAXC>(w.t2c.kw, w.t2c.kb, CN2, DD, DD, T2, DI, DI, false, RED);
+    tok_linear<MAXC>(w.t2c.vw, w.t2c.vb, CND, DD, DD, T3, DI, DI, false, RED);
     tok_small_attention(T1, T2, T3, DI, NTOK, nc, DI / NH, T4);
-    tok_linear<NTOK>(w.t2c.ow, w.t2c.ob, T4, DI, DI, T1, DD, DD, false);
+    tok_linear<NTOK>(w.t2c.ow, w.t2c.ob, T4, DI, DI, T1, DD, DD, false, RED);
     tok_add_ln(Q, Q, T1, w.n2c, eps, NTOK);
     // ---- MLP (:194-197), ReLU
-    tok_linear<NTOK>(w.l1w, w.l1b, Q, DD, DD, HID, w.mlp_dim, w.mlp_dim, true);
-    tok_linear<NTOK>(w.l2w, w.l2b, HID, w.mlp_dim, w.mlp_dim, T1, DD, DD, false);
+    tok_linear<NTOK>(w.l1w, w.l1b, Q, DD, DD, HID, w.mlp_dim, w.mlp_dim, true, RED);
+    tok_linear<NTOK>(w.l2w, w.l2b, HID, w.mlp_dim, w.mlp_dim, T1, DD, DD, false, RED);
     tok_add_ln(Q, Q, T1, w.n3, eps, NTOK);
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) qbuf[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
     // ---- keys / values of the two image-side attentions of this block (:201-212)
-    tok_linear<MAXC>(w.i2c.kw, w.i2c.kb, CN2, DD, DD, T1, DI, DI, false);
-    tok_linear<MAXC>(w.i2c.vw, w.i2c.vb, CND, DD, DD, T2, DI, DI, false);
+    tok_linear<MAXC>(w.i2c.kw, w.i2c.kb, CN2, DD, DD, T1, DI, DI, false, RED);
+    tok_linear<MAXC>(w.i2c.vw, w.i2c.vb, CND, DD, DD, T2, DI, DI, false, RED);
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.i2t.kw, w.i2t.kb, X, DD, DD, T3, DI, DI, false);
-    tok_linear<NTOK>(w.i2t.vw, w.i2t.vb, Q, DD, DD, T4, DI, DI, false);
+    tok_linear<NTOK>(w.i2t.kw, w.i2t.kb, X, DD, DD, T3, DI, DI, false, RED);
+    tok_linear<NTOK>(w.i2t.vw, w.i2t.vb, Q, DD, DD, T4, DI, DI, false, RED);
     for (int i = threadIdx.x; i < nc * DI; i += blockDim.x) {
         kc[static_cast<long long>(b) * nc * DI + i] = T1[i];
         vc[static_cast<long long>(b) * nc * DI + i] = T2[i];
@@ -471,10 +530,10 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_layer_kernel(
     }
 }
 
-__device__ void tok_mlp3(const Mlp3W& w, const float* x, int out_dim, float* t1, float* t2, float* y) {
-    tok_linear<1>(w.w0, w.b0, x, DD, DD, t1, DD, DD, true);
-    tok_linear<1>(w.w1, w.b1, t1, DD, DD, t2, DD, DD, true);
-    tok_linear<1>(w.w2, w.b2, t2, DD, DD, y, out_dim, out_dim, false);
+__device__ void tok_mlp3(const Mlp3W& w, const float* x, int out_dim, float* t1, float* t2, float* y, float* RED) {
+    tok_linear<1>(w.w0, w.b0, x, DD, DD, t1, DD, DD, true, RED);
+    tok_linear<1>(w.w1, w.b1, t1, DD, DD, t2, DD, DD, true, RED);
+    tok_linear<1>(w.w2, w.b2, t2, DD, DD, y, out_dim, out_dim, false, RED);
 }
 
 // final_attn_token_to_image + norm_final_attn (transformer_maskdecoder_edge.py:98-109), then the hyper-network MLPs,
@@ -488,21 +547,22 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_final_kernel(FinalW w, 
                                                                       float* __restrict__ iou) {
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x;
-    float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3;
+    float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3,
+          *RED = sm + SM_RED;
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
         PE[i] = tokens0[i];
         Q[i] = qbuf[static_cast<long long>(b) * NTOK * DD + i];
     }
     __syncthreads();
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false);
-    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2);
-    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED);
+    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2, RED);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED);
     tok_add_ln(Q, Q, T1, w.nf, eps, NTOK);
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) hs[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
     for (int i = 0; i <= NMASK; ++i)
-        tok_mlp3(w.hyper[i], Q + (1 + i) * DD, DE, T1, T2, T3 + i * DE);
-    tok_mlp3(w.iou, Q, NMASK, T1, T2, T3 + (NMASK + 1) * DE);
+        tok_mlp3(w.hyper[i], Q + (1 + i) * DD, DE, T1, T2, T3 + i * DE, RED);
+    tok_mlp3(w.iou, Q, NMASK, T1, T2, T3 + (NMASK + 1) * DE, RED);
     for (int i = threadIdx.x; i < (NMASK + 1) * DE; i += blockDim.x) hyper[static_cast<long long>(b) * (NMASK + 1) * DE + i] = T3[i];
     for (int i = threadIdx.x; i < NMASK; i += blockDim.x) iou[b * NMASK + i] = T3[(NMASK + 1) * DE + i];
 }
@@ -523,27 +583,27 @@ __device__ __forceinline__ int raster_to_nested(int Y, int X, int g) {
 
 template <int C>
 __global__ void __launch_bounds__(256) dec_im2col3_nested_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                 __nv_bfloat16* __restrict__ col, int g, int taps,
-                                                                 int ldcol, long long total) {
+                                                                 __nv_bfloat16* __restrict__ col, int g, int ldcol,
+                                                                 long long total) {
+    // one thread per 16-byte chunk of the output: consecutive lanes write consecutive chunks of a row
     const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (idx >= total) return;
-    const int tap = static_cast<int>(idx % taps);
-    const long long row = idx / taps;
+    const int chunks = ldcol / 8;
+    const int chunk = static_cast<int>(idx % chunks);
+    const long long row = idx / chunks;
+    const int tap = chunk / (C / 8), sub = chunk % (C / 8);
     const int P2 = 16 * g * g, S = 4 * g;
     const int n = static_cast<int>(row % P2);
     const long long img = row / P2;
-    uint4* dst = reinterpret_cast<uint4*>(col + row * ldcol + tap * C);
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    const uint4* src = nullptr;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (tap < 9) {
         int Y, X;
         nested_to_raster(n, g, Y, X);
         const int yy = Y + tap / 3 - 1, xx = X + tap % 3 - 1;
         if (yy >= 0 && yy < S && xx >= 0 && xx < S)
-            src = reinterpret_cast<const uint4*>(x + (img * P2 + raster_to_nested(yy, xx, g)) * C);
+            v = __ldg(reinterpret_cast<const uint4*>(x + (img * P2 + raster_to_nested(yy, xx, g)) * C) + sub);
     }
-#pragma unroll
-    for (int i = 0; i < C / 8; ++i) dst[i] = src ? src[i] : zero;
+    reinterpret_cast<uint4*>(col + row * ldcol)[chunk] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -689,13 +749,13 @@ struct DecFwd {
     int attn(const char* prefix, int inner, AttnW* a) {
         char p[128];
         snprintf(p, sizeof(p), "%s", prefix);
-        CVLM_TRY(getf(p, ".q_proj.weight", static_cast<long long>(inner) * DD, &a->qw));
+        CVLM_TRY(getf(p, ".q_proj.weight.t", static_cast<long long>(inner) * DD, &a->qw));
         CVLM_TRY(getf(p, ".q_proj.bias", inner, &a->qb));
-        CVLM_TRY(getf(p, ".k_proj.weight", static_cast<long long>(inner) * DD, &a->kw));
+        CVLM_TRY(getf(p, ".k_proj.weight.t", static_cast<long long>(inner) * DD, &a->kw));
         CVLM_TRY(getf(p, ".k_proj.bias", inner, &a->kb));
-        CVLM_TRY(getf(p, ".v_proj.weight", static_cast<long long>(inner) * DD, &a->vw));
+        CVLM_TRY(getf(p, ".v_proj.weight.t", static_cast<long long>(inner) * DD, &a->vw));
         CVLM_TRY(getf(p, ".v_proj.bias", inner, &a->vb));
-        CVLM_TRY(getf(p, ".out_proj.weight", static_cast<long long>(inner) * DD, &a->ow));
+        CVLM_TRY(getf(p, ".out_proj.weight.t", static_cast<long long>(inner) * DD, &a->ow));
         CVLM_TRY(getf(p, ".out_proj.bias", DD, &a->ob));
         return CVLM_OK;
     }
@@ -709,11 +769,11 @@ struct DecFwd {
     int mlp3(const char* prefix, int hidden, int out, Mlp3W* m) {
         char p[128];
         snprintf(p, sizeof(p), "%s", prefix);
-        CVLM_TRY(getf(p, ".layers.0.weight", static_cast<long long>(hidden) * DD, &m->w0));
+        CVLM_TRY(getf(p, ".layers.0.weight.t", static_cast<long long>(hidden) * DD, &m->w0));
         CVLM_TRY(getf(p, ".layers.0.bias", hidden, &m->b0));
-        CVLM_TRY(getf(p, ".layers.1.weight", static_cast<long long>(hidden) * hidden, &m->w1));
+        CVLM_TRY(getf(p, ".layers.1.weight.t", static_cast<long long>(hidden) * hidden, &m->w1));
         CVLM_TRY(getf(p, ".layers.1.bias", hidden, &m->b1));
-        CVLM_TRY(getf(p, ".layers.2.weight", static_cast<long long>(out) * hidden, &m->w2));
+        CVLM_TRY(getf(p, ".layers.2.weight.t", static_cast<long long>(out) * hidden, &m->w2));
         CVLM_TRY(getf(p, ".layers.2.bias", out, &m->b2));
         return CVLM_OK;
     }
@@ -757,7 +817,7 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(CVLM_ERR_ARG, "decoder_forward: workspace must be 1 KiB aligned");
     const int g = c.grid, T = g * g, nc = c.cond_tokens;
     const long long M = static_cast<long long>(T) * batch, P1 = 4 * M, P2 = 16 * M;
-    if (P2 * 9 >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
+    if (P2 * 72 / 256 >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
     char* base = static_cast<char*>(workspace);
     auto F32 = [&](long long off) { return reinterpret_cast<float*>(base + off); };
     auto PTR = [&](long long off) { return static_cast<void*>(base + off); };
@@ -817,10 +877,10 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         snprintf(sub, sizeof(sub), "%s.norm4", pre);                      CVLM_TRY(f.norm(sub, DD, &n4));
         snprintf(sub, sizeof(sub), "%s.norm4_cond", pre);                 CVLM_TRY(f.norm(sub, DD, &n4c));
         snprintf(sub, sizeof(sub), "%s.mlp.lin1", pre);
-        CVLM_TRY(f.getf(sub, ".weight", static_cast<long long>(c.mlp_dim) * DD, &lw.l1w));
+        CVLM_TRY(f.getf(sub, ".weight.t", static_cast<long long>(c.mlp_dim) * DD, &lw.l1w));
         CVLM_TRY(f.getf(sub, ".bias", c.mlp_dim, &lw.l1b));
         snprintf(sub, sizeof(sub), "%s.mlp.lin2", pre);
-        CVLM_TRY(f.getf(sub, ".weight", static_cast<long long>(c.mlp_dim) * DD, &lw.l2w));
+        CVLM_TRY(f.getf(sub, ".weight.t", static_cast<long long>(c.mlp_dim) * DD, &lw.l2w));
         CVLM_TRY(f.getf(sub, ".bias", DD, &lw.l2b));
         const void *wk, *wv, *wqc, *woc, *wqt, *wot;
         snprintf(sub, sizeof(sub), "%s.cross_attn_token_to_image", pre);
@@ -906,14 +966,14 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         CVLM_TRY(f.geth("embedding_maskfeature.3", ".wp", static_cast<long long>(DE) * 9 * DQ, &w3));
         CVLM_TRY(f.getf("embedding_maskfeature.3", ".bias", DE, &b3));
         ++f.launches;
-        dec_im2col3_nested_kernel<DE><<<static_cast<unsigned>((P2 * 10 + 255) / 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 10, k0, P2 * 10);
+        dec_im2col3_nested_kernel<DE><<<static_cast<unsigned>((P2 * (k0 / 8) + 255) / 256), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, k0, P2 * (k0 / 8));
         CVLM_CUDA(cudaGetLastError());
         CVLM_TRY(f.gemm(PTR(ws.col), P2, k0, w0, DQ, b0, nullptr, PTR(ws.m1)));
         CVLM_TRY(ln_rows<DQ>(f, F32(ws.m1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.mh), nullptr, P2));
         ++f.launches;
-        dec_im2col3_nested_kernel<DQ><<<static_cast<unsigned>((P2 * 9 + 255) / 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 9, 9 * DQ, P2 * 9);
+        dec_im2col3_nested_kernel<DQ><<<static_cast<unsigned>((P2 * (9 * DQ / 8) + 255) / 256), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 9 * DQ, P2 * (9 * DQ / 8));
         CVLM_CUDA(cudaGetLastError());
         CVLM_TRY(f.gemm(PTR(ws.col), P2, 9 * DQ, w3, DE, b3, F32(ws.ef), PTR(ws.ee)));
     }

@@ -94,7 +94,8 @@ class MLP(nn.Module):
 def pack_decoder_weights(sd: Dict[str, torch.Tensor], depth: int, device) -> Dict[str, torch.Tensor]:
     """Device tensors registered with ``cvlm_decoder_set_tensor``:
 
-    * every fp32 parameter under its reference name (the token-side kernels read them as they are);
+    * every fp32 parameter under its reference name, and every nn.Linear weight also transposed as ``<name>.weight.t``
+      ([in, out]: what the token-side kernels stream);
     * ``tokens`` fp32 [6,256] = [iou_token; mask_tokens; edge_token] (mask_decoder_edge.py:157);
     * ``<attention>.{k,v,q,out}_proj.weight.bf16`` for the projections applied to the 4096 image tokens;
     * k2 s2 transposed convolutions as GEMMs: ``<conv>.wp`` bf16 [(dy*2+dx)*Cout + o, i] = W[i,o,dy,dx] and ``<conv>.bp``
@@ -107,6 +108,8 @@ def pack_decoder_weights(sd: Dict[str, torch.Tensor], depth: int, device) -> Dic
     b16 = lambda t: t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
     for k, v in sd.items():
         out[k] = f32(v)
+        if v.dim() == 2 and k.endswith(".weight") and k not in ("iou_token.weight", "mask_tokens.weight", "edge_token.weight"):
+            out[k + ".t"] = out[k].t().contiguous()          # nn.Linear weights, transposed for the token-side kernels
     out["tokens"] = torch.cat([out["iou_token.weight"], out["mask_tokens.weight"], out["edge_token.weight"]], 0).contiguous()
     img_side = []
     for i in range(depth):
@@ -171,7 +174,7 @@ class MaskDecoder(nn.Module):
             nn.ConvTranspose2d(transformer_dim // 4, transformer_dim // 8, 3, 1, 1),
         )
         self.sigmoid = nn.Sigmoid()
-        self.max_chunk = 8              # images per C-ABI call; bounds the workspace (~155 MB / image at g = 64)
+        self.max_chunk = 32             # images per C-ABI call; bounds the workspace (~155 MB / image at g = 64)
         self._handles: Dict[Tuple[int, int], int] = {}
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None

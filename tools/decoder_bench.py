@@ -1,0 +1,112 @@
+"""Mask decoder timing on one GPU: decoder alone on resident embeddings, and the encoder -> decoder ->
+postprocess cascade.  CUDA events on the launching stream, warm-up first, inputs larger than L2 at the default batch.
+Prints one JSON line.  --cpu also times the oracle (CPU restatement of the reference decoder) on one image.
+
+    python tools/decoder_bench.py [--batch 32] [--steps 10] [--warmup 3] [--cascade] [--cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from camouflaged_vlm_b200 import mask_decoder as md      # noqa: E402
+
+
+def seeded_decoder():
+    # weights only: the seeded state lives with the oracle, which this tool may not import on the product path;
+    # plain normal init with the same scale is enough for timing
+    dec = md.MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                         transformer=md.TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)).eval()
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n, p in dec.named_parameters():
+            p.copy_(torch.randn(p.shape, generator=gen) * 0.05 + (1.0 if (p.dim() == 1 and n.endswith("weight")) else 0.0))
+    return dec.cuda()
+
+
+def timed(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunk", type=int, default=32)
+    ap.add_argument("--cascade", action="store_true")
+    ap.add_argument("--cpu", action="store_true")
+    args = ap.parse_args()
+    B, g = args.batch, 64
+    dec = seeded_decoder()
+    dec.max_chunk = args.chunk
+    gen = torch.Generator().manual_seed(1)
+    emb = torch.randn(B, 256, g, g, generator=gen).cuda()
+    pe = torch.randn(1, 256, g, g, generator=gen).cuda()
+    sparse = torch.randn(B, 2, 256, generator=gen).cuda()
+    dense = (torch.randn(1, 256, 1, 1, generator=gen) * 0.05).cuda().expand(B, -1, g, g)
+    out = {}
+
+    def decode():
+        with torch.no_grad():
+            m, e, i = dec(emb, [], pe, sparse, dense, False)
+            out["m"] = md.postprocess_masks(m, 1024, 1024, 1024)
+
+    ms = timed(decode, args.steps, args.warmup)
+    line = {"metric": "mask_decoder_img_per_s", "value": B / ms * 1e3, "unit": "img/s", "ms_per_step": ms, "batch": B,
+            "chunk": args.chunk, "steps": args.steps, "warmup": args.warmup, "gpu_launches": dec.last_launch_count + 1,
+            "config": {"workload": "MaskDecoder_Edge + postprocess_masks, 64x64x256 embeddings -> 1024x1024 logits",
+                       "l2": "inputs + workspace of a chunk (> 1 GB) exceed L2"}}
+    if args.cascade:
+        from camouflaged_vlm_b200 import PRESETS, build_encoder
+        from camouflaged_vlm_b200.synth import seeded_images, seeded_state_dict
+        cfg = PRESETS["vit_h"]
+        enc = build_encoder(cfg).eval()
+        enc.load_state_dict(seeded_state_dict(cfg, 0), strict=True)
+        enc = enc.cuda()
+        x = seeded_images(cfg, 1).cuda().expand(B, -1, -1, -1).contiguous()
+
+        def cascade():
+            with torch.no_grad():
+                f, _ = enc(x, interm=True)
+                m, e, i = dec(f, [], pe, sparse, dense, False)
+                out["m"] = md.postprocess_masks(m, 1024, 1024, 1024)
+
+        def encode():
+            with torch.no_grad():
+                enc(x, interm=True)
+
+        ms_e = timed(encode, max(3, args.steps // 2), args.warmup)
+        ms_c = timed(cascade, max(3, args.steps // 2), args.warmup)
+        line["cascade"] = {"encoder_ms": ms_e, "encoder_decoder_postprocess_ms": ms_c, "img_per_s": B / ms_c * 1e3,
+                           "decoder_share": 1.0 - ms_e / ms_c}
+    if args.cpu:
+        from oracle import mask_decoder_oracle as mdo     # cpu_baseline leg only
+        sd = mdo.seeded_decoder_state(0)
+        e1 = emb[:1].cpu()
+        mdo.decode_all(sd, e1)
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            mdo.binary_mask(mdo.decode_all(sd, e1)["masks"][:, 0:1], 1024)
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{n} images, oracle decode_all + postprocess on the host"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
