@@ -116,33 +116,51 @@ __global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restric
                                                           const float* __restrict__ pos, int T, float* out_f32,
                                                           __nv_bfloat16* __restrict__ out_b16,
                                                           __nv_bfloat16* __restrict__ out_pos_b16, long long rows) {
-    constexpr int PER = C / 32;
-    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    // a row is covered by C/4 lanes holding 4 consecutive channels each: one warp normalises 128/C rows
+    constexpr int LPR = C / 4;              // lanes per row: 64 (C = 256, two passes of the warp) or 16 (C = 64)
+    constexpr int RPW = LPR >= 32 ? 1 : 32 / LPR;
+    constexpr int PASS = LPR >= 32 ? LPR / 32 : 1;
     const int lane = threadIdx.x & 31;
-    float v[PER];
+    const long long row = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * RPW + (RPW > 1 ? lane / LPR : 0);
+    const bool live = row < rows;
+    const int c0 = (RPW > 1 ? lane % LPR : lane) * 4;
+    float4 v[PASS];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        v[j] = x[row * C + lane + 32 * j];
-        s += v[j];
+    for (int j = 0; j < PASS; ++j) {
+        v[j] = live ? *reinterpret_cast<const float4*>(x + row * C + c0 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
-    const float mean = warp_sum(s) * (1.f / C);
+#pragma unroll
+    for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        v[j] -= mean;
-        q = fmaf(v[j], v[j], q);
+    for (int j = 0; j < PASS; ++j) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += fmaf(v[j].x, v[j].x, v[j].y * v[j].y) + fmaf(v[j].z, v[j].z, v[j].w * v[j].w);
     }
-    const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + eps);
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int c = lane + 32 * j;
-        float y = fmaf(v[j] * rstd, gamma[c], beta[c]);
-        if (gelu) y = gelu_exact(y);
-        if (out_f32) out_f32[row * C + c] = y;
-        if (out_b16) out_b16[row * C + c] = __float2bfloat16_rn(y);
-        if (out_pos_b16) out_pos_b16[row * C + c] = __float2bfloat16_rn(y + pos[(row % T) * C + c]);
+    for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q * (1.f / C) + eps);
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < PASS; ++j) {
+        const int c = c0 + 128 * j;
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+        float4 y = make_float4(fmaf(v[j].x * rstd, gm.x, bt.x), fmaf(v[j].y * rstd, gm.y, bt.y),
+                               fmaf(v[j].z * rstd, gm.z, bt.z), fmaf(v[j].w * rstd, gm.w, bt.w));
+        if (gelu) y = make_float4(gelu_exact(y.x), gelu_exact(y.y), gelu_exact(y.z), gelu_exact(y.w));
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+        if (out_b16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+            *reinterpret_cast<uint2*>(out_b16 + row * C + c) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+        if (out_pos_b16) {
+            const float4 p = *reinterpret_cast<const float4*>(pos + (row % T) * C + c);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(y.x + p.x, y.y + p.y), hi = __floats2bfloat162_rn(y.z + p.z, y.w + p.w);
+            *reinterpret_cast<uint2*>(out_pos_b16 + row * C + c) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
     }
 }
 
@@ -581,29 +599,26 @@ __device__ __forceinline__ int raster_to_nested(int Y, int X, int g) {
     return ((((Y >> 2) * g + (X >> 2)) * 4 + ((Y >> 1) & 1) * 2 + ((X >> 1) & 1)) << 2) + (Y & 1) * 2 + (X & 1);
 }
 
-template <int C>
+template <int C, int LDCOL>
 __global__ void __launch_bounds__(256) dec_im2col3_nested_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                 __nv_bfloat16* __restrict__ col, int g, int ldcol,
-                                                                 long long total) {
-    // one thread per 16-byte chunk of the output: consecutive lanes write consecutive chunks of a row
-    const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int chunks = ldcol / 8;
-    const int chunk = static_cast<int>(idx % chunks);
-    const long long row = idx / chunks;
-    const int tap = chunk / (C / 8), sub = chunk % (C / 8);
+                                                                 __nv_bfloat16* __restrict__ col, int g) {
+    // one thread per 16-byte chunk of the output: consecutive lanes write consecutive chunks of a row.  grid.y = image.
+    constexpr int CHUNKS = LDCOL / 8;
     const int P2 = 16 * g * g, S = 4 * g;
-    const int n = static_cast<int>(row % P2);
-    const long long img = row / P2;
+    const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= static_cast<unsigned>(P2) * CHUNKS) return;
+    const int n = static_cast<int>(idx / CHUNKS), chunk = static_cast<int>(idx % CHUNKS);
+    const int tap = chunk / (C / 8), sub = chunk % (C / 8);
+    const long long base = static_cast<long long>(blockIdx.y) * P2;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (tap < 9) {
         int Y, X;
         nested_to_raster(n, g, Y, X);
         const int yy = Y + tap / 3 - 1, xx = X + tap % 3 - 1;
         if (yy >= 0 && yy < S && xx >= 0 && xx < S)
-            v = __ldg(reinterpret_cast<const uint4*>(x + (img * P2 + raster_to_nested(yy, xx, g)) * C) + sub);
+            v = __ldg(reinterpret_cast<const uint4*>(x + (base + raster_to_nested(yy, xx, g)) * C) + sub);
     }
-    reinterpret_cast<uint4*>(col + row * ldcol)[chunk] = v;
+    reinterpret_cast<uint4*>(col + (base + n) * LDCOL)[chunk] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -647,18 +662,18 @@ __global__ void __launch_bounds__(256) dec_masks_kernel(const float* __restrict_
 // F.interpolate(mode="bilinear", align_corners=False) on fp32 NCHW planes (postprocess_masks,
 // models/sam_maskdecoder_edge.py:380-387)
 __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                              int ih, int iw, int oh, int ow, float sh, float sw,
-                                                              long long total) {
-    const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int ox = static_cast<int>(idx % ow), oy = static_cast<int>((idx / ow) % oh);
-    const long long plane = idx / (static_cast<long long>(ow) * oh);
+                                                              int ih, int iw, int oh, int ow, float sh, float sw) {
+    // block = 64 x 4 output pixels of plane blockIdx.z
+    const int ox = blockIdx.x * 64 + (threadIdx.x & 63), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ox >= ow || oy >= oh) return;
     const float fy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
     const int y0 = min(static_cast<int>(fy), ih - 1), x0 = min(static_cast<int>(fx), iw - 1);
     const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
     const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const float* p = in + plane * ih * iw;
-    out[idx] = hy * (hx * p[y0 * iw + x0] + lx * p[y0 * iw + x1]) + ly * (hx * p[y1 * iw + x0] + lx * p[y1 * iw + x1]);
+    const float* p = in + static_cast<long long>(blockIdx.z) * ih * iw;
+    out[(static_cast<long long>(blockIdx.z) * oh + oy) * ow + ox] =
+        hy * (hx * __ldg(p + y0 * iw + x0) + lx * __ldg(p + y0 * iw + x1)) +
+        ly * (hx * __ldg(p + y1 * iw + x0) + lx * __ldg(p + y1 * iw + x1));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -795,7 +810,8 @@ template <int C>
 int ln_rows(DecFwd& f, const float* x, const float* gamma, const float* beta, float eps, int gelu, const float* pos, int T,
             float* out_f32, void* out_b16, void* out_pos_b16, long long rows) {
     ++f.launches;
-    dec_ln_rows_kernel<C><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, f.stream>>>(
+    constexpr int rows_per_block = 8 * (C >= 128 ? 1 : 128 / C);
+    dec_ln_rows_kernel<C><<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), 256, 0, f.stream>>>(
         x, gamma, beta, eps, gelu, pos, T, out_f32, static_cast<__nv_bfloat16*>(out_b16),
         static_cast<__nv_bfloat16*>(out_pos_b16), rows);
     CVLM_CUDA(cudaGetLastError());
@@ -966,14 +982,15 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         CVLM_TRY(f.geth("embedding_maskfeature.3", ".wp", static_cast<long long>(DE) * 9 * DQ, &w3));
         CVLM_TRY(f.getf("embedding_maskfeature.3", ".bias", DE, &b3));
         ++f.launches;
-        dec_im2col3_nested_kernel<DE><<<static_cast<unsigned>((P2 * (k0 / 8) + 255) / 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, k0, P2 * (k0 / 8));
+        const int P2i = 16 * T;      // pixels of one image
+        dec_im2col3_nested_kernel<DE, 10 * DE><<<dim3((P2i * (k0 / 8) + 255) / 256, batch), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g);
         CVLM_CUDA(cudaGetLastError());
         CVLM_TRY(f.gemm(PTR(ws.col), P2, k0, w0, DQ, b0, nullptr, PTR(ws.m1)));
         CVLM_TRY(ln_rows<DQ>(f, F32(ws.m1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.mh), nullptr, P2));
         ++f.launches;
-        dec_im2col3_nested_kernel<DQ><<<static_cast<unsigned>((P2 * (9 * DQ / 8) + 255) / 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g, 9 * DQ, P2 * (9 * DQ / 8));
+        dec_im2col3_nested_kernel<DQ, 9 * DQ><<<dim3((P2i * (9 * DQ / 8) + 255) / 256, batch), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g);
         CVLM_CUDA(cudaGetLastError());
         CVLM_TRY(f.gemm(PTR(ws.col), P2, 9 * DQ, w3, DE, b3, F32(ws.ef), PTR(ws.ee)));
     }
@@ -989,9 +1006,9 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
 
 int bilinear_resize_launch(const float* in, float* out, long long planes, int ih, int iw, int oh, int ow, cudaStream_t stream) {
     if (!in || !out || planes < 1 || ih < 1 || iw < 1 || oh < 1 || ow < 1) return set_error(CVLM_ERR_ARG, "bilinear_resize: bad arguments");
-    const long long total = planes * oh * ow;
-    bilinear_resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-        in, out, ih, iw, oh, ow, static_cast<float>(ih) / oh, static_cast<float>(iw) / ow, total);
+    if (planes > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "bilinear_resize: more than 65535 planes in one call");
+    bilinear_resize_kernel<<<dim3((ow + 63) / 64, (oh + 3) / 4, static_cast<unsigned>(planes)), 256, 0, stream>>>(
+        in, out, ih, iw, oh, ow, static_cast<float>(ih) / oh, static_cast<float>(iw) / ow);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
