@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-interm", action="store_true", help="call forward(x) instead of forward(x, interm=True)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-decoder", action="store_true", help="skip the mask-decoder / cascade leg (SURVEY 8 f1)")
     return ap.parse_args()
 
 
@@ -331,6 +332,49 @@ def run_ours(args):
                        + ("NCCL all_gather_into_tensor of the embeddings, " if world > 1 else "")
                        + "device -> pinned host copy of each rank's embeddings (per chunk, same copy stream); whole-job bytes"}
 
+    # ---- the next row of the hot path: the mask decoder on this step's embeddings, and the
+    # encoder -> decoder -> postprocess cascade; reported beside the headline, not part of it
+    f1 = None
+    if rank == 0 and world == 1 and not args.skip_decoder and cfg.out_chans == 256 and cfg.grid % 8 == 0:
+        from camouflaged_vlm_b200 import mask_decoder as md
+        dec = md.build_mask_decoder(seed=0).to(dev)
+        gen = torch.Generator().manual_seed(1)
+        pe = torch.randn(1, 256, cfg.grid, cfg.grid, generator=gen).to(dev)
+        sparse = torch.randn(B, 2, 256, generator=gen).to(dev)
+        dense = (torch.randn(1, 256, 1, 1, generator=gen) * 0.05).to(dev).expand(B, -1, cfg.grid, cfg.grid)
+        with torch.no_grad():
+            emb = model(x_dev)
+
+        def decode(e):
+            with torch.no_grad():
+                m, _, _ = dec(e, [], pe, sparse, dense, False)
+                return md.postprocess_masks(m, cfg.img_size, cfg.img_size, cfg.img_size)
+
+        def cascade():
+            with torch.no_grad():
+                f, _ = model(x_dev, interm=True)
+            return decode(f)
+
+        res = {}
+        for name, fn, n in (("decoder", lambda: decode(emb), 10), ("cascade", cascade, max(3, K // 2))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / n
+        f1 = {"metric": "mask_decoder_img_per_s", "value": B / res["decoder"] * 1e3, "unit": UNIT,
+              "ms_per_step": res["decoder"], "gpu_launches": int(dec.last_launch_count) + 1,
+              "workload": f"MaskDecoder_Edge + postprocess_masks on {B} embeddings [256,{cfg.grid},{cfg.grid}] -> "
+                          f"{cfg.img_size}x{cfg.img_size} logits, 2 prompt tokens per image, random-init weights",
+              "cascade": {"value": B / res["cascade"] * 1e3, "unit": UNIT, "ms_per_step": res["cascade"],
+                          "what": "ImageEncoderViT.forward(x, interm=True) -> MaskDecoder_Edge -> postprocess_masks, inputs resident"}}
+        del dec
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -347,7 +391,7 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels,
+            "cpu_baseline": cpu, "kernels": kernels, "mask_decoder": f1,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

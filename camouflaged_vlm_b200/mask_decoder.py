@@ -290,6 +290,19 @@ class MaskDecoder(nn.Module):
 MaskDecoder_Edge = MaskDecoder      # the name the cascade imports it under (models/sam_maskdecoder_edge.py:10)
 
 
+def build_mask_decoder(seed: Optional[int] = None) -> MaskDecoder:
+    """The decoder as the cascade constructs it (models/sam_maskdecoder_edge.py:137-148).  With ``seed`` the parameters are
+    re-drawn from a seeded normal (std 0.05, norm weights around 1): synthetic weights for benchmarks."""
+    dec = MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                      transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)).eval()
+    if seed is not None:
+        gen = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for n, p in dec.named_parameters():
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.05 + (1.0 if (p.dim() == 1 and n.endswith("weight")) else 0.0))
+    return dec
+
+
 def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     """F.interpolate(x, size, mode="bilinear", align_corners=False) for fp32 NCHW CUDA tensors (csrc/decoder.cu)."""
     if not x.is_cuda:

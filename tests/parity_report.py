@@ -53,7 +53,47 @@ def main(out_path):
     rep["vit_h_downstream_mask_iou"] = mdo.iou(mdo.binary_mask(got, 1024), mdo.binary_mask(want, 1024))
     rep["vit_h_downstream_logits_rel_l2"] = orc.rel_l2(got, want)
     print("downstream mask IoU:", rep["vit_h_downstream_mask_iou"], "logits rel-L2:", rep["vit_h_downstream_logits_rel_l2"])
-    del m
+    # the CUDA mask decoder (8 f1): on the reference's small golden, on seeded full-size inputs against the oracle, and
+    # the whole cascade (CUDA encoder -> CUDA decoder) against the reference cascade's logits
+    from camouflaged_vlm_b200 import mask_decoder as md
+    dsd = mdo.seeded_decoder_state(0)
+    dec = md.MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                         transformer=md.TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)).eval()
+    dec.load_state_dict({k: v for k, v in dsd.items() if not k.startswith("probe.")}, strict=True)
+    dec = dec.cuda()
+
+    def run_dec(e, sparse=None):
+        B, _, gg, _ = e.shape
+        sp = dsd["probe.sparse"].expand(B, -1, -1) if sparse is None else sparse
+        dense = dsd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(B, -1, gg, gg)
+        with torch.no_grad():
+            return dec.predict_all(e.cuda(), mdo.dense_pe(dsd, gg).cuda(), sp.cuda(), dense.cuda())
+
+    gs = np.load(os.path.join(GOLDEN, "decoder_small.npz"))
+    mk, ed, io = run_dec(torch.from_numpy(gs["emb"]))
+    d = {"small_golden": {"masks_rel_l2": orc.rel_l2(mk.cpu(), torch.from_numpy(gs["masks_all"])),
+                          "edge_rel_l2": orc.rel_l2(ed.cpu(), torch.from_numpy(gs["edge"])),
+                          "iou_pred_max_abs": float((io.cpu() - torch.from_numpy(gs["iou"])).abs().max()),
+                          "mask_iou": mdo.iou(mdo.binary_mask(mk[:, 0:1].cpu(), 256),
+                                              mdo.binary_mask(torch.from_numpy(gs["logits"]), 256))}}
+    gen = torch.Generator().manual_seed(2)
+    e64 = torch.randn(2, 256, 64, 64, generator=gen)
+    sp64 = torch.randn(2, 2, 256, generator=gen)
+    mk, ed, io = run_dec(e64, sp64)
+    full = []
+    for b in range(2):
+        w = mdo.decode_all(dsd, e64[b:b + 1], sp64[b:b + 1])
+        full.append({"masks_rel_l2": orc.rel_l2(mk[b:b + 1].cpu(), w["masks"]), "edge_rel_l2": orc.rel_l2(ed[b:b + 1].cpu(), w["edge"]),
+                     "hs_rel_l2": orc.rel_l2(dec.last_hs[b:b + 1].cpu(), w["hs"]),
+                     "iou_pred_max_abs": float((io[b:b + 1].cpu() - w["iou"]).abs().max()),
+                     "mask_iou": mdo.iou(mdo.binary_mask(mk[b:b + 1, 0:1].cpu(), 1024), mdo.binary_mask(w["masks"][:, 0:1], 1024))})
+    d["full_size_vs_oracle"] = full
+    mk, _, _ = run_dec(emb.float())
+    d["cascade_vit_h_vs_reference"] = {"logits_rel_l2": orc.rel_l2(mk[:, 0:1].cpu(), want),
+                                       "mask_iou": mdo.iou(mdo.binary_mask(mk[:, 0:1].cpu(), 1024), mdo.binary_mask(want, 1024))}
+    rep["mask_decoder"] = d
+    print("mask decoder:", json.dumps(d))
+    del m, dec
     torch.cuda.empty_cache()
     # how much does the cuFFT high-pass depend on the batch it is computed in?
     cfg = PRESETS["vit_h"]

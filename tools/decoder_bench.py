@@ -17,15 +17,7 @@ from camouflaged_vlm_b200 import mask_decoder as md      # noqa: E402
 
 
 def seeded_decoder():
-    # weights only: the seeded state lives with the oracle, which this tool may not import on the product path;
-    # plain normal init with the same scale is enough for timing
-    dec = md.MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
-                         transformer=md.TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)).eval()
-    gen = torch.Generator().manual_seed(0)
-    with torch.no_grad():
-        for n, p in dec.named_parameters():
-            p.copy_(torch.randn(p.shape, generator=gen) * 0.05 + (1.0 if (p.dim() == 1 and n.endswith("weight")) else 0.0))
-    return dec.cuda()
+    return md.build_mask_decoder(seed=0).cuda()
 
 
 def timed(fn, steps, warmup):

@@ -19,7 +19,7 @@ tail -c 3000 $O/bench_$TAG.json | tee -a $O/round_$TAG.log
 tail -5 $O/bench_$TAG.err | tee -a $O/round_$TAG.log
 if [ "$2" == "noncu" ]; then exit 0; fi
 KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|attn_global_tc2_kernel|attn_window_tc2_kernel|layernorm_kernel|ln_finalize_kernel|im2col|cast_bf16_kernel|cast_pad_rows_kernel|adapter_embed_kernel|layernorm_nchw_kernel'
-BENCH="python bench.py --steps 1 --warmup 3 --batch 32 --skip-cpu-baseline --skip-e2e"
+BENCH="python bench.py --steps 1 --warmup 3 --batch 32 --skip-cpu-baseline --skip-e2e --skip-decoder"
 echo "=== ncu launch list" | tee -a $O/round_$TAG.log
 $BENCH > $O/plain_$TAG.log 2>&1 && \
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 729 -c 243 --csv \
