@@ -1,5 +1,6 @@
 /*
- * cvlm.h -- C ABI of the B200-native SAM-Adapter image encoder (libcvlm_b200.so).
+ * cvlm.h -- C ABI of the B200-native SAM-Adapter image encoder, its input pipeline and its mask decoder
+ * (libcvlm_b200.so).
  *
  * The reference (intcomp/camouflaged-vlm) has no FFI or plugin layer on this path: its boundary is
  * the Python class models/mmseg/models/sam/image_encoder.py:25 `ImageEncoderViT`, called as
