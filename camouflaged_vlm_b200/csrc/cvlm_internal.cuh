@@ -61,6 +61,12 @@ struct GemmArgs {
     int b_k_off = 0;
     long long batch_rows = 0;
     int act_abs = 0;           // fp32 path: store |value|
+    // Implicit 3x3 convolution (stride 1, padding 1) over an NHWC map with 64 channels stored with a one-pixel ZERO
+    // border: A = bf16 [m, 64] holds the rows of images of conv_pitch x conv_pitch padded pixels, B = [n, 9 * 64] with
+    // column (ty*3+tx)*64 + c.  K-block t of output row r reads A row r + (t/3 - 1) * conv_pitch + (t%3 - 1) (zero outside
+    // [0, m)), so no im2col matrix is ever written.  Output rows at border pixels are meaningless; the caller zeroes or
+    // ignores them.  k1 must be 576.
+    int conv_pitch = 0;
 };
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 

@@ -17,7 +17,8 @@
 //   kimg / vimg / qi  fp32 [M,128]   projections for the cross attentions;  ao bf16 [M,128] attention output
 //   Up-scaled maps keep NESTED pixel order: pixel (y,x) of the g x g map owns the contiguous rows
 //   ((y*g+x)*4 + s1)*4 + s2, s = 2*dy+dx of each transposed convolution, so a k2 s2 transposed convolution is a plain
-//   reshape of the GEMM output.  im2col and the final mask kernel translate to raster order.
+//   reshape of the GEMM output.  The two 3x3 convolutions run as implicit GEMMs over zero-bordered RASTER maps
+//   (GemmArgs::conv_pitch); dec_pad_raster_kernel and the final mask kernel translate between the two orders.
 #include <string.h>
 
 #include <string>
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restric
                                                           const float* __restrict__ beta, float eps, int gelu,
                                                           const float* __restrict__ pos, int T, float* out_f32,
                                                           __nv_bfloat16* __restrict__ out_b16,
-                                                          __nv_bfloat16* __restrict__ out_pos_b16, long long rows) {
+                                                          __nv_bfloat16* __restrict__ out_pos_b16, long long rows,
+                                                          int pad_pitch) {
     // a row is covered by C/4 lanes holding 4 consecutive channels each: one warp normalises 128/C rows
     constexpr int LPR = C / 4;              // lanes per row: 64 (C = 256, two passes of the warp) or 16 (C = 64)
     constexpr int RPW = LPR >= 32 ? 1 : 32 / LPR;
@@ -144,9 +146,20 @@ __global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restric
     for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = 1.f / sqrtf(q * (1.f / C) + eps);
     if (!live) return;
+    // padded raster maps (pad_pitch > 0): the border rows feed the next implicit convolution and must stay zero
+    bool border = false;
+    if (pad_pitch > 0) {
+        const int pr = static_cast<int>(row % (static_cast<long long>(pad_pitch) * pad_pitch));
+        const int py = pr / pad_pitch, px = pr % pad_pitch;
+        border = py == 0 || py == pad_pitch - 1 || px == 0 || px == pad_pitch - 1;
+    }
 #pragma unroll
     for (int j = 0; j < PASS; ++j) {
         const int c = c0 + 128 * j;
+        if (border) {
+            if (out_b16) *reinterpret_cast<uint2*>(out_b16 + row * C + c) = make_uint2(0u, 0u);
+            continue;
+        }
         const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
         float4 y = make_float4(fmaf(v[j].x * rstd, gm.x, bt.x), fmaf(v[j].y * rstd, gm.y, bt.y),
                                fmaf(v[j].z * rstd, gm.z, bt.z), fmaf(v[j].w * rstd, gm.w, bt.w));
@@ -586,64 +599,55 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_final_kernel(FinalW w, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// 3x3 im2col over a map stored in nested pixel order (see the header): rows stay in nested order, column
-// (ty*3+tx)*C + c holds channel c of pixel (Y+ty-1, X+tx-1) or zero outside the map; columns >= 9C are zero padding.
-// One thread per (pixel, tap).
+// The 3x3 (transposed) convolutions run as implicit GEMMs (GemmArgs::conv_pitch) over maps in PADDED RASTER order:
+// image b, pixel (Y, X) of the S x S map lives at row b*(S+2)^2 + (Y+1)*(S+2) + (X+1) of a [*, 64] bf16 matrix whose
+// border rows are zero.  raster -> nested index helper, and the kernel that re-lays the nested 32-channel up-scaled map
+// out that way (channels 32..63 and the border are zero).  One thread per 16-byte chunk; grid.y = image.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nested_to_raster(int n, int g, int& Y, int& X) {
-    const int p = n >> 4, s1 = (n >> 2) & 3, s2 = n & 3;
-    Y = (p / g) * 4 + (s1 >> 1) * 2 + (s2 >> 1);
-    X = (p % g) * 4 + (s1 & 1) * 2 + (s2 & 1);
-}
 __device__ __forceinline__ int raster_to_nested(int Y, int X, int g) {
     return ((((Y >> 2) * g + (X >> 2)) * 4 + ((Y >> 1) & 1) * 2 + ((X >> 1) & 1)) << 2) + (Y & 1) * 2 + (X & 1);
 }
 
-template <int C, int LDCOL>
-__global__ void __launch_bounds__(256) dec_im2col3_nested_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                 __nv_bfloat16* __restrict__ col, int g) {
-    // one thread per 16-byte chunk of the output: consecutive lanes write consecutive chunks of a row.  grid.y = image.
-    constexpr int CHUNKS = LDCOL / 8;
-    const int P2 = 16 * g * g, S = 4 * g;
+__global__ void __launch_bounds__(256) dec_pad_raster_kernel(const __nv_bfloat16* __restrict__ x_nested,
+                                                             __nv_bfloat16* __restrict__ out, int g) {
+    const int S = 4 * g, pitch = S + 2, PP = pitch * pitch;
     const unsigned idx = blockIdx.x * 256u + threadIdx.x;
-    if (idx >= static_cast<unsigned>(P2) * CHUNKS) return;
-    const int n = static_cast<int>(idx / CHUNKS), chunk = static_cast<int>(idx % CHUNKS);
-    const int tap = chunk / (C / 8), sub = chunk % (C / 8);
-    const long long base = static_cast<long long>(blockIdx.y) * P2;
+    if (idx >= static_cast<unsigned>(PP) * 8u) return;
+    const int pr = static_cast<int>(idx >> 3), chunk = static_cast<int>(idx & 7);
+    const int Y = pr / pitch - 1, X = pr % pitch - 1;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (tap < 9) {
-        int Y, X;
-        nested_to_raster(n, g, Y, X);
-        const int yy = Y + tap / 3 - 1, xx = X + tap % 3 - 1;
-        if (yy >= 0 && yy < S && xx >= 0 && xx < S)
-            v = __ldg(reinterpret_cast<const uint4*>(x + (base + raster_to_nested(yy, xx, g)) * C) + sub);
-    }
-    reinterpret_cast<uint4*>(col + (base + n) * LDCOL)[chunk] = v;
+    if (chunk < DE / 8 && Y >= 0 && Y < S && X >= 0 && X < S)
+        v = __ldg(reinterpret_cast<const uint4*>(x_nested + (static_cast<long long>(blockIdx.y) * S * S + raster_to_nested(Y, X, g)) * DE) + chunk);
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(blockIdx.y) * PP + pr) * DQ)[chunk] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // masks = hyper[:4] . upscaled, edge = sigmoid(hyper[4] . edge_embedding), masks = masks * edge + masks
-// (mask_decoder_edge.py:176-183).  One thread per output pixel in raster order; inputs in nested order.
+// (mask_decoder_edge.py:176-183).  One thread per output pixel in raster order; `up` and the edge features are in
+// nested order, the output of embedding_maskfeature in padded raster order.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_masks_kernel(const float* __restrict__ up, const float* __restrict__ ee,
-                                                        const float* __restrict__ hyper, float* __restrict__ masks,
-                                                        float* __restrict__ edge, int g) {
+                                                        const float* __restrict__ ef, const float* __restrict__ hyper,
+                                                        float* __restrict__ masks, float* __restrict__ edge, int g) {
     __shared__ float hy[(NMASK + 1) * DE];
-    const int b = blockIdx.y, S = 4 * g, P2 = S * S;
+    const int b = blockIdx.y, S = 4 * g, P2 = S * S, pitch = S + 2;
     if (threadIdx.x < (NMASK + 1) * DE) hy[threadIdx.x] = hyper[b * (NMASK + 1) * DE + threadIdx.x];
     __syncthreads();
     const int pix = blockIdx.x * 256 + threadIdx.x;
     if (pix >= P2) return;
     const int Y = pix / S, X = pix % S;
-    const long long row = static_cast<long long>(b) * P2 + raster_to_nested(Y, X, g);
+    const long long row = static_cast<long long>(b) * P2 + raster_to_nested(Y, X, g);                 // nested maps
+    const long long prow = static_cast<long long>(b) * pitch * pitch + (Y + 1) * pitch + (X + 1);     // padded raster map
     float u[DE], e[DE];
     const float4* upp = reinterpret_cast<const float4*>(up + row * DE);
-    const float4* eep = reinterpret_cast<const float4*>(ee + row * DE);
+    const float4* eep = reinterpret_cast<const float4*>(ee + prow * DE);
+    const float4* efp = reinterpret_cast<const float4*>(ef + row * DE);
 #pragma unroll
     for (int i = 0; i < DE / 4; ++i) {
-        const float4 a = upp[i], c = eep[i];
+        const float4 a = upp[i], c = eep[i], f = efp[i];
         u[4 * i] = a.x; u[4 * i + 1] = a.y; u[4 * i + 2] = a.z; u[4 * i + 3] = a.w;
-        e[4 * i] = c.x; e[4 * i + 1] = c.y; e[4 * i + 2] = c.z; e[4 * i + 3] = c.w;
+        // edge_embedding = embedding_maskfeature(upscaled) + edge features (mask_decoder_edge.py:168)
+        e[4 * i] = c.x + f.x; e[4 * i + 1] = c.y + f.y; e[4 * i + 2] = c.z + f.z; e[4 * i + 3] = c.w + f.w;
     }
     float ed = 0.f;
 #pragma unroll
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __res
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 struct DecWorkspace {
-    long long keys, kb, kpb, eb, pos, kimg, vimg, qi, ao, u1, h1, up, upb, ef, col, m1, mh, ee, qbuf, kc, vc, ktok, vtok,
+    long long keys, kb, kpb, eb, pos, kimg, vimg, qi, ao, u1, h1, up, upb, ef, upp, m1, mh, ee, qbuf, kc, vc, ktok, vtok,
         hyper, hs, total;
 };
 
@@ -707,10 +711,11 @@ DecWorkspace plan(const cvlm_decoder_config& c, int batch) {
     w.up = take(P2 * DE * 4);
     w.upb = take(P2 * DE * 2);
     w.ef = take(P2 * DE * 4);
-    w.col = take(P2 * 9 * DQ * 2);
-    w.m1 = take(P2 * DQ * 4);
-    w.mh = take(P2 * DQ * 2);
-    w.ee = take(P2 * DE * 4);
+    const long long PP = static_cast<long long>(batch) * (4 * c.grid + 2) * (4 * c.grid + 2);   // padded raster pixels
+    w.upp = take(PP * DQ * 2);
+    w.m1 = take(PP * DQ * 4);
+    w.mh = take(PP * DQ * 2);
+    w.ee = take(PP * DE * 4);
     w.qbuf = take(static_cast<long long>(batch) * NTOK * DD * 4);
     w.kc = take(static_cast<long long>(batch) * MAXC * DI * 4);
     w.vc = take(static_cast<long long>(batch) * MAXC * DI * 4);
@@ -794,9 +799,10 @@ struct DecFwd {
     }
     // out[M, n] = a[M, k] * w[n, k]^T + bias (+ residual), fp32 output unless out_bf16; optional GELU / bf16 copy
     int gemm(const void* a, long long m, int k, const void* w, int n, const float* bias, const float* residual, void* out,
-             int gelu = 0, void* copy = nullptr) {
+             int gelu = 0, void* copy = nullptr, int conv_pitch = 0) {
         GemmArgs g;
-        g.a1 = a; g.lda1 = k; g.b1 = w; g.ldb1 = k; g.k1 = k;
+        g.a1 = a; g.lda1 = conv_pitch > 0 ? DQ : k; g.b1 = w; g.ldb1 = k; g.k1 = k;
+        g.conv_pitch = conv_pitch;
         g.m = static_cast<int>(m); g.n = n;
         g.bias = bias; g.residual = residual; g.ldr = n;
         g.out = out; g.ldo = n; g.out_bf16 = 0; g.act_gelu = gelu;
@@ -808,12 +814,12 @@ struct DecFwd {
 
 template <int C>
 int ln_rows(DecFwd& f, const float* x, const float* gamma, const float* beta, float eps, int gelu, const float* pos, int T,
-            float* out_f32, void* out_b16, void* out_pos_b16, long long rows) {
+            float* out_f32, void* out_b16, void* out_pos_b16, long long rows, int pad_pitch = 0) {
     ++f.launches;
     constexpr int rows_per_block = 8 * (C >= 128 ? 1 : 128 / C);
     dec_ln_rows_kernel<C><<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), 256, 0, f.stream>>>(
         x, gamma, beta, eps, gelu, pos, T, out_f32, static_cast<__nv_bfloat16*>(out_b16),
-        static_cast<__nv_bfloat16*>(out_pos_b16), rows);
+        static_cast<__nv_bfloat16*>(out_pos_b16), rows, pad_pitch);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
@@ -832,8 +838,8 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         return set_error(CVLM_ERR_WORKSPACE, "decoder_forward: workspace %lld < %lld bytes", workspace_bytes, ws.total);
     if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(CVLM_ERR_ARG, "decoder_forward: workspace must be 1 KiB aligned");
     const int g = c.grid, T = g * g, nc = c.cond_tokens;
-    const long long M = static_cast<long long>(T) * batch, P1 = 4 * M, P2 = 16 * M;
-    if (P2 * 72 / 256 >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
+    const long long M = static_cast<long long>(T) * batch, P1 = 4 * M;
+    if (static_cast<long long>(batch) * (4 * g + 2) * (4 * g + 2) >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
     char* base = static_cast<char*>(workspace);
     auto F32 = [&](long long off) { return reinterpret_cast<float*>(base + off); };
     auto PTR = [&](long long off) { return static_cast<void*>(base + off); };
@@ -970,33 +976,31 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         CVLM_TRY(ln_rows<DQ>(f, F32(ws.u1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.h1), nullptr, P1));
         CVLM_TRY(f.gemm(PTR(ws.h1), P1, DQ, w3, 4 * DE, b3, nullptr, PTR(ws.up), 1, PTR(ws.upb)));
     }
-    // ---- embedding_maskfeature(upscaled) + edge features (:168, :88-93): two 3x3 transposed convolutions (s1 p1)
+    // ---- embedding_maskfeature(upscaled) (:168, :88-93): two 3x3 s1 p1 transposed convolutions = 3x3 convolutions with
+    // the flipped kernel, as implicit GEMMs over zero-bordered raster maps (no im2col); the edge features are added by the
+    // mask kernel
     {
         const void *w0, *w3;
         const float *b0, *b3, *lw, *lb;
-        const int k0 = 10 * DE;   // 9 taps x 32 channels padded to a multiple of 64
-        CVLM_TRY(f.geth("embedding_maskfeature.0", ".wp", static_cast<long long>(DQ) * k0, &w0));
+        const int pitch = 4 * g + 2;
+        const long long PP = static_cast<long long>(batch) * pitch * pitch;
+        CVLM_TRY(f.geth("embedding_maskfeature.0", ".wp", static_cast<long long>(DQ) * 9 * DQ, &w0));
         CVLM_TRY(f.getf("embedding_maskfeature.0", ".bias", DQ, &b0));
         CVLM_TRY(f.getf("embedding_maskfeature.1", ".weight", DQ, &lw));
         CVLM_TRY(f.getf("embedding_maskfeature.1", ".bias", DQ, &lb));
         CVLM_TRY(f.geth("embedding_maskfeature.3", ".wp", static_cast<long long>(DE) * 9 * DQ, &w3));
         CVLM_TRY(f.getf("embedding_maskfeature.3", ".bias", DE, &b3));
         ++f.launches;
-        const int P2i = 16 * T;      // pixels of one image
-        dec_im2col3_nested_kernel<DE, 10 * DE><<<dim3((P2i * (k0 / 8) + 255) / 256, batch), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g);
+        dec_pad_raster_kernel<<<dim3((pitch * pitch * 8 + 255) / 256, batch), 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(PTR(ws.upb)), static_cast<__nv_bfloat16*>(PTR(ws.upp)), g);
         CVLM_CUDA(cudaGetLastError());
-        CVLM_TRY(f.gemm(PTR(ws.col), P2, k0, w0, DQ, b0, nullptr, PTR(ws.m1)));
-        CVLM_TRY(ln_rows<DQ>(f, F32(ws.m1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.mh), nullptr, P2));
-        ++f.launches;
-        dec_im2col3_nested_kernel<DQ, 9 * DQ><<<dim3((P2i * (9 * DQ / 8) + 255) / 256, batch), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(PTR(ws.mh)), static_cast<__nv_bfloat16*>(PTR(ws.col)), g);
-        CVLM_CUDA(cudaGetLastError());
-        CVLM_TRY(f.gemm(PTR(ws.col), P2, 9 * DQ, w3, DE, b3, F32(ws.ef), PTR(ws.ee)));
+        CVLM_TRY(f.gemm(PTR(ws.upp), PP, 9 * DQ, w0, DQ, b0, nullptr, PTR(ws.m1), 0, nullptr, pitch));
+        CVLM_TRY(ln_rows<DQ>(f, F32(ws.m1), lw, lb, c.ln2d_eps, 1, nullptr, 1, nullptr, PTR(ws.mh), nullptr, PP, pitch));
+        CVLM_TRY(f.gemm(PTR(ws.mh), PP, 9 * DQ, w3, DE, b3, nullptr, PTR(ws.ee), 0, nullptr, pitch));
     }
     // ---- masks, edge
     ++f.launches;
-    dec_masks_kernel<<<dim3((16 * T + 255) / 256, batch), 256, 0, stream>>>(F32(ws.up), F32(ws.ee), F32(ws.hyper), masks, edge, g);
+    dec_masks_kernel<<<dim3((16 * T + 255) / 256, batch), 256, 0, stream>>>(F32(ws.up), F32(ws.ee), F32(ws.ef), F32(ws.hyper), masks, edge, g);
     CVLM_CUDA(cudaGetLastError());
     dec->last_launches = f.launches;
     return CVLM_OK;

@@ -62,6 +62,9 @@ struct GemmEpi {
     long long batch_rows;
     int b_k_off;
     int act_abs;                  // fp32 path: store |value|
+    int conv_pitch;               // > 0: implicit 3x3 convolution over a zero-bordered raster map (GemmArgs::conv_pitch)
+    int n_run;                    // run-time-epilogue kernel: accumulator columns the MMA really computes (64, 128, 192 or
+                                  // 256): a narrow output does not pay for a 256-wide tile on the tensor pipe
 };
 
 // Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
@@ -183,24 +186,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
+            // bytes of B one box brings in: the run-time kernel trims the box to the n_run columns it computes
+            const uint32_t b_tx = (FEAT & F_RARE) ? static_cast<uint32_t>(ep.n_run) * (PAIR ? BK : 2 * BK) : B_BYTES;
             for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
                 const int bidx = (FEAT & F_RARE) ? tile / ep.tiles_per_batch : 0, tl = tile - bidx * ep.tiles_per_batch;
                 const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM;
-                const int n0 = (tl % tiles_n) * BN + (PAIR ? cta_rank * (BN / 2) : 0);
+                // PAIR: each CTA stages its half of the B rows the instruction reads (n_run / 2 of them)
+                const int n0 = (tl % tiles_n) * BN + (PAIR ? cta_rank * (((FEAT & F_RARE) ? ep.n_run : BN) / 2) : 0);
                 const int bk = (FEAT & F_RARE) ? bidx * ep.b_k_off : 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const bool second = kb >= kblocks1;
                     const int kc = (second ? kb - kblocks1 : kb) * BK;
+                    // implicit 3x3 convolution: k-block kb is tap (kb / 3, kb % 3); its A tile is the same 64 channels
+                    // of the pixel rows shifted by that tap (rows outside the map read as zero)
+                    int a_col = kc, a_row = m0;
+                    if ((FEAT & F_RARE) && ep.conv_pitch > 0) {
+                        a_col = 0;
+                        a_row = m0 + (kb / 3 - 1) * ep.conv_pitch + (kb % 3 - 1);
+                    }
                     if (PAIR) {
                         // the leader arms its barrier with the bytes of both CTAs; both CTAs' copies complete on it
-                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (A_STAGE + B_BYTES));
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * (A_STAGE + b_tx));
                         const uint32_t lead_bar = full_bar(stage) & kPeerBitMask;
-                        tma_load_2d_pair(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, lead_bar, kc, m0);
+                        tma_load_2d_pair(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, lead_bar, a_col, a_row);
                         tma_load_2d_pair(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, lead_bar, kc + bk, n0);
                     } else {
-                        mbar_arrive_expect_tx(full_bar(stage), A_STAGE + B_BYTES);
-                        tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), kc, m0);
+                        mbar_arrive_expect_tx(full_bar(stage), A_STAGE + b_tx);
+                        tma_load_2d(sA + stage * A_STAGE, second ? &tmA2 : &tmA1, full_bar(stage), a_col, a_row);
                         tma_load_2d(sB + stage * B_BYTES, second ? &tmB2 : &tmB1, full_bar(stage), kc + bk, n0);
                     }
                     if (++stage == NSTAGE) {
@@ -213,7 +226,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
     } else if (warp == 1) {
         // ===================== MMA issuer (single lane; PAIR: of the leader CTA only) =====================
         if (cta_rank == 0 && elect_one_sync()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+            const uint32_t idesc = umma_idesc_bf16(TILE_M, (FEAT & F_RARE) ? ep.n_run : BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -259,7 +272,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         const bool has_res = (FEAT & F_STATIC) ? (FEAT & F_RES) != 0 : ep.residual != nullptr;
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
-        const int half = ew >> 2;           // which EPI_COLS of the 256 accumulator columns
+        const int half = ew >> 2;           // which half of the accumulator columns
+        // the two warps of a lane quadrant split the columns the MMA really computed (n_run <= 256 in the run-time kernel)
+        const int epi_cols = (FEAT & F_RARE) ? ep.n_run / 2 : EPI_COLS;
+        const int epi_chunks = (FEAT & F_RARE) ? ep.n_run / 64 : EPI_CHUNKS;
         const uint32_t stg = staging + ew * 4096;
         const float* __restrict__ bias = ep.bias;
         int iter = 0;
@@ -287,8 +303,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
             mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < EPI_CHUNKS; ++c) {
-                const int col0 = n0 + half * EPI_COLS + c * 32;
+            for (int c = 0; c < epi_chunks; ++c) {
+                const int col0 = n0 + half * epi_cols + c * 32;
                 // fp32 path: issue the chunk's 8 residual loads first, as one batch.  out may alias residual
                 // (in-place shortcut add), so loads interleaved with the stores below would be serialised
                 // behind them by the compiler and expose a full memory latency per row group.
@@ -323,9 +339,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                     }
                 }
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * EPI_COLS + c * 32, v);
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * epi_cols + c * 32, v);
                 tmem_ld_wait(v);
-                if (c == EPI_CHUNKS - 1) {
+                if (c == epi_chunks - 1) {
                     // all of this warp's TMEM reads are done: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -613,9 +629,15 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const char* mode = getenv("CVLM_GEMM_MODE");
     const int pair_tiles = nbatch * ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
     const bool pair = mode && mode[0] == 'p' ? true : mode && mode[0] == '1' ? false : pair_tiles >= num_sms() / 2;
-    const int b_box = pair ? BN / 2 : BN;
+    // narrow outputs (n <= 192) run the run-time-epilogue kernel with the MMA, the B box and the epilogue trimmed to
+    // n_run columns: rows of a TMA box that fall outside the tensor are zero-filled at ~11 cycles each (measured on the
+    // decoder's N = 64 convolutions: 1.1 us per k-block with a 256-row box against 64 real rows), far slower than real rows
+    const int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
+    const int b_box = pair ? n_run / 2 : n_run;
     CUtensorMap tA1, tB1, tA2, tB2;
-    CVLM_TRY(make_tensor_map(&tA1, a.a1, a.m, a.k1, a.lda1, BM));
+    if (a.conv_pitch > 0 && (a.k1 != 9 * BK || a.k2 > 0 || nbatch > 1 || a.lda1 != BK || a.ln_rows))
+        return set_error(CVLM_ERR_ARG, "gemm: the implicit 3x3 mode needs A = [m, %d] (lda %d), k1 = %d, one K segment, no batching", BK, BK, 9 * BK);
+    CVLM_TRY(make_tensor_map(&tA1, a.a1, a.m, a.conv_pitch > 0 ? BK : a.k1, a.lda1, BM));
     // batched mode: batch b reads B columns [b * b_k_off, b * b_k_off + k); with b_k_off == k the map ends exactly
     // where the last batch entry does, so ragged K edges still zero-fill
     if (nbatch > 1 && (a.b_k_off != a.k1 || (a.k2 > 0 && a.k2 != a.k1) || a.k1 % BK))
@@ -642,18 +664,18 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
                static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
                reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
-               a.act_abs};
+               a.act_abs, a.conv_pitch, n_run};
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     const int tiles_n = (a.n + BN - 1) / BN;
     const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;
     ep.tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = nbatch * tiles_m * tiles_n;
     // the exact shape of this call's epilogue; launch_variant maps the four block GEMMs to their own kernels
-    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0;
+    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0;
     const bool producer = a.copy_bf16 != nullptr && a.stat_out != nullptr;
     int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.residual ? F_RES : 0) |
                (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0);
-    if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || !a.bias) feat = V_ANY;
+    if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || !a.bias || n_run < BN) feat = V_ANY;
     return launch_variant(pair, feat, total_tiles, stream, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, nbatch * tiles_m, tiles_n, ep);
 }
 

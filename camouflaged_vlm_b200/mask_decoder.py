@@ -100,8 +100,8 @@ def pack_decoder_weights(sd: Dict[str, torch.Tensor], depth: int, device) -> Dic
     * ``<attention>.{k,v,q,out}_proj.weight.bf16`` for the projections applied to the 4096 image tokens;
     * k2 s2 transposed convolutions as GEMMs: ``<conv>.wp`` bf16 [(dy*2+dx)*Cout + o, i] = W[i,o,dy,dx] and ``<conv>.bp``
       fp32 = bias tiled 4x;
-    * 3x3 s1 p1 transposed convolutions as im2col GEMMs: ``<conv>.wp`` bf16 [o, (ty*3+tx)*Cin + i] = W[i,o,2-ty,2-tx],
-      K padded with zeros to a multiple of 64.
+    * 3x3 s1 p1 transposed convolutions as implicit GEMMs (3x3 convolutions with the flipped kernel):
+      ``<conv>.wp`` bf16 [o, (ty*3+tx)*64 + i] = W[i,o,2-ty,2-tx], 64 input channels per tap (zero padded).
     """
     out: Dict[str, torch.Tensor] = {}
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -128,11 +128,9 @@ def pack_decoder_weights(sd: Dict[str, torch.Tensor], depth: int, device) -> Dic
     for n in ("embedding_maskfeature.0", "embedding_maskfeature.3"):
         w = f32(sd[n + ".weight"])                      # [Cin, Cout, 3, 3]
         cin, cout = w.shape[0], w.shape[1]
-        wp = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cout, 9 * cin)
-        kpad = (9 * cin + 63) // 64 * 64
-        full = torch.zeros(cout, kpad, device=device, dtype=torch.float32)
-        full[:, :9 * cin] = wp
-        out[n + ".wp"] = full.to(torch.bfloat16).contiguous()
+        full = torch.zeros(cout, 9, 64, device=device, dtype=torch.float32)      # 64 input channels per tap (zero padded)
+        full[:, :, :cin] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cout, 9, cin)
+        out[n + ".wp"] = full.reshape(cout, 9 * 64).to(torch.bfloat16).contiguous()
     return out
 
 
@@ -174,7 +172,7 @@ class MaskDecoder(nn.Module):
             nn.ConvTranspose2d(transformer_dim // 4, transformer_dim // 8, 3, 1, 1),
         )
         self.sigmoid = nn.Sigmoid()
-        self.max_chunk = 32             # images per C-ABI call; bounds the workspace (~155 MB / image at g = 64)
+        self.max_chunk = 32             # images per C-ABI call; bounds the workspace (~85 MB / image at g = 64)
         self._handles: Dict[Tuple[int, int], int] = {}
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None

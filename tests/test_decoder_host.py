@@ -73,9 +73,9 @@ def test_transposed_convolutions_as_gemms():
     y = torch.randn(1, 32, 4 * g, 4 * g)
     cols = F.unfold(y, 3, padding=1)[0]                                               # [32*9, P] ordered (c, ty, tx)
     cols = cols.reshape(32, 9, -1).permute(2, 1, 0).reshape(-1, 288)                  # [P, (ty*3+tx)*32 + c]
-    wp = packed["embedding_maskfeature.0.wp"].float()
-    assert wp.shape == (64, 320) and float(wp[:, 288:].abs().max()) == 0.0
-    got = (cols @ wp[:, :288].t() + sd["embedding_maskfeature.0.bias"]).t().reshape(1, 64, 4 * g, 4 * g)
+    wp = packed["embedding_maskfeature.0.wp"].float().reshape(64, 9, 64)             # 64 channels per tap, zero padded
+    assert float(wp[:, :, 32:].abs().max()) == 0.0
+    got = (cols @ wp[:, :, :32].reshape(64, 288).t() + sd["embedding_maskfeature.0.bias"]).t().reshape(1, 64, 4 * g, 4 * g)
     want = F.conv_transpose2d(y, sd["embedding_maskfeature.0.weight"], sd["embedding_maskfeature.0.bias"], stride=1, padding=1)
     assert float((got - want).abs().max()) < 1e-4
     assert packed["embedding_maskfeature.3.wp"].shape == (32, 576)

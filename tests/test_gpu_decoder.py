@@ -55,7 +55,7 @@ def test_decoder_matches_reference_golden():
     m3, _, i3 = run(dec, sd, emb, multimask=True)                  # mask_decoder_edge.py:133-139: tokens 1..3
     assert m3.shape == (1, 3, 64, 64) and i3.shape == (1, 3)
     assert rel_l2(m3.cpu(), torch.from_numpy(g["masks_all"])[:, 1:]) < TOL
-    assert dec.last_launch_count == 38
+    assert dec.last_launch_count == 37
 
 
 def test_decoder_token_side_is_fp32_accurate():
