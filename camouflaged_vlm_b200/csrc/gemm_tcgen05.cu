@@ -630,8 +630,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const int pair_tiles = nbatch * ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
     const bool pair = mode && mode[0] == 'p' ? true : mode && mode[0] == '1' ? false : pair_tiles >= num_sms() / 2;
     // narrow outputs (n <= 192) run the run-time-epilogue kernel with the MMA, the B box and the epilogue trimmed to
-    // n_run columns: rows of a TMA box that fall outside the tensor are zero-filled at ~11 cycles each (measured on the
-    // decoder's N = 64 convolutions: 1.1 us per k-block with a 256-row box against 64 real rows), far slower than real rows
+    // n_run columns.  The B box matters most: with a 256-row box over a 64-row weight matrix every k-block took 1.1 us
+    // (0.5 us with the 128-row boxes of a CTA pair) however little the MMA had to do -- the time followed the number of
+    // box rows beyond the tensor, ~11 cycles per zero-filled row (decoder 3x3 convolutions, profiles/decoder_bench_r1x.json).
+    // The 5-D window boxes of the attention kernel show no such cost (tools/win_oob_probe.py).
     const int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
     const int b_box = pair ? n_run / 2 : n_run;
     CUtensorMap tA1, tB1, tA2, tB2;

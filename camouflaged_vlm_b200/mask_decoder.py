@@ -172,7 +172,7 @@ class MaskDecoder(nn.Module):
             nn.ConvTranspose2d(transformer_dim // 4, transformer_dim // 8, 3, 1, 1),
         )
         self.sigmoid = nn.Sigmoid()
-        self.max_chunk = 32             # images per C-ABI call; bounds the workspace (~85 MB / image at g = 64)
+        self.max_chunk = 32             # images per C-ABI call; bounds the workspace (~88 MB / image at g = 64)
         self._handles: Dict[Tuple[int, int], int] = {}
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None

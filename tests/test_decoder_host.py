@@ -80,3 +80,28 @@ def test_transposed_convolutions_as_gemms():
     assert float((got - want).abs().max()) < 1e-4
     assert packed["embedding_maskfeature.3.wp"].shape == (32, 576)
     assert packed["tokens"].shape == (6, 256)
+
+
+def test_decoder_handle_workspace_and_config_validation():
+    import ctypes as C
+    from camouflaged_vlm_b200 import _lib
+    lib = _lib.load()
+
+    def cfg(**kw):
+        c = _lib.DecoderConfigC()
+        c.dim, c.heads, c.mlp_dim, c.depth, c.num_mask_tokens, c.grid, c.cond_tokens = 256, 8, 2048, 2, 4, 64, 2
+        c.ln_eps, c.ln2d_eps = 1e-5, 1e-6
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    h = C.c_void_p()
+    assert lib.cvlm_decoder_create(C.byref(cfg()), C.byref(h)) == 0
+    per_image = [lib.cvlm_decoder_workspace_bytes(h, b) / b for b in (1, 8, 32)]
+    assert all(80e6 < x < 100e6 for x in per_image), per_image          # no im2col matrix: < 100 MB per image
+    assert lib.cvlm_decoder_workspace_bytes(h, 0) < 0
+    assert lib.cvlm_decoder_destroy(h) == 0
+    for bad in (dict(dim=128), dict(heads=4), dict(grid=12), dict(grid=0), dict(cond_tokens=9), dict(mlp_dim=100), dict(depth=0)):
+        h2 = C.c_void_p()
+        assert lib.cvlm_decoder_create(C.byref(cfg(**bad)), C.byref(h2)) == -3, bad
+        assert lib.cvlm_last_error()

@@ -20,6 +20,51 @@ def seeded_decoder():
     return md.build_mask_decoder(seed=0).cuda()
 
 
+def algorithmic_bytes_per_image(g, depth=2):
+    """HBM bytes each launch of the decoder has to move for one image (inputs read once + outputs written once per kernel,
+    weights and the shared image_pe excluded), by stage.  DESIGN.md 5.6 lists the same stages."""
+    T, P1, P2, PP = g * g, 4 * g * g, 16 * g * g, (4 * g + 2) ** 2
+    f32, b16 = 4, 2
+    st = {}
+    st["prep"] = T * 256 * (f32 + f32 + 3 * b16)
+    convt = lambda: T * 256 * b16 + T * 256 * f32 + (P1 * 64 * f32 + P1 * 64 * b16) + P1 * 64 * b16          # GEMM, LN, GEMM input
+    st["embedding_encoder"] = convt() + P2 * 32 * f32
+    layer = 2 * (T * 256 * b16 + T * 128 * f32)                       # k / v projections for the token side
+    layer += 2 * T * 128 * f32                                        # token kernel reads them
+    layer += 2 * ((T * 256 * b16 + T * 128 * f32)                     # q projection
+                  + (T * 128 * f32 + T * 128 * b16)                   # few-key attention
+                  + (T * 128 * b16 + 2 * T * 256 * f32)               # out projection + shortcut, in place
+                  + (T * 256 * f32 + T * 256 * (f32 + 2 * b16)))      # LayerNorm, fp32 + two bf16 copies
+    st["transformer_layers"] = depth * layer
+    st["final_attention"] = 2 * (T * 256 * b16 + T * 128 * f32) + 2 * T * 128 * f32
+    st["output_upscaling"] = convt() + P2 * 32 * (f32 + b16)
+    st["embedding_maskfeature"] = (P2 * 32 * b16 + PP * 64 * b16) + (PP * 64 * b16 + PP * 64 * f32) + \
+                                  (PP * 64 * f32 + PP * 64 * b16) + (PP * 64 * b16 + PP * 32 * f32)
+    st["masks"] = P2 * 32 * f32 * 2 + PP * 32 * f32 + P2 * 5 * f32
+    st["postprocess"] = P2 * f32 + (16 * g) ** 2 * f32               # one mask plane up-sampled to the 16g x 16g image
+    return st
+
+
+def hbm_roofline(B, g, ms):
+    peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    peak, src = 6456.5, "fallback: the figure MEASURED_PEAKS.json held in round 1"
+    try:
+        pj = json.load(open(peaks_path))
+        for k in ("hbm_gbs", "hbm_gbps", "hbm_copy_gbs"):
+            if k in pj:
+                peak, src = float(pj[k]), "measured (MEASURED_PEAKS.json)"
+                break
+    except Exception:
+        pass
+    st = algorithmic_bytes_per_image(g)
+    total = sum(st.values()) * B
+    ach = total / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
+            "traffic": None, "algorithmic_bytes_per_image": st,
+            "note": "whole decoder: bytes every launch must read and write once (weights excluded) / measured time; "
+                    "the token kernels and the implicit convolutions are not HBM-bound (DESIGN.md 5.6)"}
+
+
 def timed(fn, steps, warmup):
     for _ in range(warmup):
         fn()
@@ -62,6 +107,7 @@ def main():
             "chunk": args.chunk, "steps": args.steps, "warmup": args.warmup, "gpu_launches": dec.last_launch_count + 1,
             "config": {"workload": "MaskDecoder_Edge + postprocess_masks, 64x64x256 embeddings -> 1024x1024 logits",
                        "l2": "inputs + workspace of a chunk (> 1 GB) exceed L2"}}
+    line["roofline"] = hbm_roofline(B, g, ms)
     if args.cascade:
         from camouflaged_vlm_b200 import PRESETS, build_encoder
         from camouflaged_vlm_b200.synth import seeded_images, seeded_state_dict
