@@ -24,7 +24,11 @@
 #include <string>
 #include <unordered_map>
 
+#include <cooperative_groups.h>
+
 #include "cvlm_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 struct cvlm_decoder {
     cvlm_decoder_config cfg;
@@ -44,6 +48,7 @@ constexpr int NMASK = 4;
 constexpr int MAXC = 8;        // prompt tokens per image supported by the kernels
 constexpr int DQ = 64, DE = 32;
 constexpr int TOK_THREADS = 512;
+constexpr int RED_FLOATS = 16 * NTOK * 192;     // scratch of the token kernels (floats)
 
 inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
@@ -259,68 +264,56 @@ struct FinalW {
     Mlp3W iou;
 };
 
+// The token kernels run one thread-block CLUSTER per image (1, 2, 4 or 8 CTAs, chosen by the host so that the batch fills
+// the machine once).  Every CTA keeps a full copy of the (tiny) activations in its own shared memory; a linear layer or the
+// token->image attention is split across the ranks, and each rank writes its slice into every rank's copy through
+// distributed shared memory.  Cheap steps (LayerNorm, 6x6 attention, adds) are simply repeated by every rank on identical
+// data.  Each slice has exactly one producer, so all copies stay bit-identical and nothing depends on scheduling.
+struct Cl {
+    int rank, size;
+};
+__device__ __forceinline__ void cl_sync(const Cl& cl) {
+    if (cl.size > 1) cg::this_cluster().sync();
+    else __syncthreads();
+}
+__device__ __forceinline__ float* cl_remote(float* p, const Cl& cl, int r) {
+    return cl.size > 1 ? cg::this_cluster().map_shared_rank(p, r) : p;
+}
+constexpr int SYNC_BEFORE = 1;   // cluster barrier before this step publishes (everyone is done reading the destination)
+constexpr int SYNC_AFTER = 2;    // cluster barrier after it (the destination is complete everywhere)
+constexpr int SYNC_BOTH = 3;
+
 // ys[t][o] = act(sum_k xs[t][k] * W[o][k] + b[o]) for t < NT, with the weight stored TRANSPOSED (Wt[k][o], packed by the
-// host as "<name>.weight.t"): a thread owns four adjacent output columns, so a warp reads 512 contiguous bytes of one
-// weight row per load; the activations are shared-memory broadcasts.  When there are fewer column groups than threads
-// the K range is split over up to 8 thread groups whose partial sums meet in `red` ([8][NT][out] floats at most) and are
-// added in a fixed order (results do not depend on scheduling).  out % 4 == 0, in % 32 == 0.
+// host as "<name>.weight.t").  Rank r of the cluster owns a contiguous block of output columns; inside the CTA a thread
+// owns four adjacent columns (a warp reads contiguous runs of a weight row) and a slice of the K range, the partial sums
+// meet in `red` and are added in a fixed order.  Several independent linears may share one pair of barriers (`sync`).
+// out % 4 == 0, in % 32 == 0.
 template <int NT>
 __device__ void tok_linear(const float* __restrict__ Wt, const float* __restrict__ bias, const float* xs, int ldx, int in,
-                           float* ys, int ldy, int out, bool relu, float* red) {
+                           float* ys, int ldy, int out, bool relu, float* red, const Cl& cl, int sync) {
     const int nthr = blockDim.x, tid = threadIdx.x;
-    const int cthreads = out / 4;
-    if (cthreads >= nthr) {
-        // wide layer (MLP lin1): every thread walks the whole K range, several passes over the columns
-        for (int c = tid; c < cthreads; c += nthr) {
-            float acc[NT][4];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-            const float4* wp = reinterpret_cast<const float4*>(Wt) + c;
-#pragma unroll 2
-            for (int k = 0; k < in; k += 4) {
-                float4 w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) w[u] = __ldg(wp + static_cast<long long>(k + u) * cthreads);
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + k);
-                    acc[t][0] = fmaf(xv.x, w[0].x, acc[t][0]); acc[t][1] = fmaf(xv.x, w[0].y, acc[t][1]);
-                    acc[t][2] = fmaf(xv.x, w[0].z, acc[t][2]); acc[t][3] = fmaf(xv.x, w[0].w, acc[t][3]);
-                    acc[t][0] = fmaf(xv.y, w[1].x, acc[t][0]); acc[t][1] = fmaf(xv.y, w[1].y, acc[t][1]);
-                    acc[t][2] = fmaf(xv.y, w[1].z, acc[t][2]); acc[t][3] = fmaf(xv.y, w[1].w, acc[t][3]);
-                    acc[t][0] = fmaf(xv.z, w[2].x, acc[t][0]); acc[t][1] = fmaf(xv.z, w[2].y, acc[t][1]);
-                    acc[t][2] = fmaf(xv.z, w[2].z, acc[t][2]); acc[t][3] = fmaf(xv.z, w[2].w, acc[t][3]);
-                    acc[t][0] = fmaf(xv.w, w[3].x, acc[t][0]); acc[t][1] = fmaf(xv.w, w[3].y, acc[t][1]);
-                    acc[t][2] = fmaf(xv.w, w[3].z, acc[t][2]); acc[t][3] = fmaf(xv.w, w[3].w, acc[t][3]);
-                }
-            }
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) bv = *reinterpret_cast<const float4*>(bias + 4 * c);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                float4 y = make_float4(acc[t][0] + bv.x, acc[t][1] + bv.y, acc[t][2] + bv.z, acc[t][3] + bv.w);
-                if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
-                *reinterpret_cast<float4*>(ys + t * ldy + 4 * c) = y;
-            }
-        }
-        __syncthreads();
-        return;
+    const int per = ((out + cl.size * 4 - 1) / (cl.size * 4)) * 4;           // columns per rank
+    const int c_lo = min(out, cl.rank * per), ncol = min(out, c_lo + per) - c_lo;
+    const int cthreads = ncol / 4;
+    int split = 1;
+    if (cthreads > 0 && cthreads < nthr) {
+        split = nthr / cthreads;
+        if (split > in / 4) split = in / 4;
+        while (split > 1 && (in % (split * 4) || split * NT * ncol > RED_FLOATS)) split >>= 1;
     }
-    int split = nthr / cthreads;
-    if (split > 8) split = 8;
-    while (split > 1 && in % (split * 4)) split >>= 1;
     const int kchunk = in / split;
-    const int ks = tid / cthreads, c = tid % cthreads;
-    if (ks < split) {
+    // ---- partial sums of this rank's columns
+    for (int c = tid % max(cthreads, 1), ks = tid / max(cthreads, 1); cthreads > 0 && c < cthreads && ks < split; c += nthr) {
         float acc[NT][4];
 #pragma unroll
         for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-        const float4* wp = reinterpret_cast<const float4*>(Wt) + c;
+        const float4* wp = reinterpret_cast<const float4*>(Wt + c_lo) + c;
+        const int ldw = out / 4;
 #pragma unroll 2
         for (int k = ks * kchunk; k < (ks + 1) * kchunk; k += 4) {
             float4 w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) w[u] = __ldg(wp + static_cast<long long>(k + u) * cthreads);
+            for (int u = 0; u < 4; ++u) w[u] = __ldg(wp + static_cast<long long>(k + u) * ldw);
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const float4 xv = *reinterpret_cast<const float4*>(xs + t * ldx + k);
@@ -334,18 +327,41 @@ __device__ void tok_linear(const float* __restrict__ Wt, const float* __restrict
                 acc[t][2] = fmaf(xv.w, w[3].z, acc[t][2]); acc[t][3] = fmaf(xv.w, w[3].w, acc[t][3]);
             }
         }
+        if (split > 1) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-            *reinterpret_cast<float4*>(red + (ks * NT + t) * out + 4 * c) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+            for (int t = 0; t < NT; ++t)
+                *reinterpret_cast<float4*>(red + (ks * NT + t) * ncol + 4 * c) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+        } else {
+            // wide layer: this thread owns whole columns; finish them here and keep them in `red` as [NT][ncol]
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bv = *reinterpret_cast<const float4*>(bias + c_lo + 4 * c);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float4 y = make_float4(acc[t][0] + bv.x, acc[t][1] + bv.y, acc[t][2] + bv.z, acc[t][3] + bv.w);
+                if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+                *reinterpret_cast<float4*>(red + t * ncol + 4 * c) = y;
+            }
+        }
     }
     __syncthreads();
-    for (int i = tid; i < NT * out; i += nthr) {
-        const int t = i / out, o = i % out;
-        float y = bias ? bias[o] : 0.f;
-        for (int s2 = 0; s2 < split; ++s2) y += red[(s2 * NT + t) * out + o];
-        ys[t * ldy + o] = relu ? fmaxf(y, 0.f) : y;
+    if (split > 1) {
+        // fold the K slices: red[0][t][o] <- act(bias + sum_s red[s][t][o])
+        for (int i = tid; i < NT * ncol; i += nthr) {
+            const int o = i % ncol;
+            float y = bias ? bias[c_lo + o] : 0.f;
+            for (int s2 = 0; s2 < split; ++s2) y += red[s2 * NT * ncol + i];
+            red[i] = relu ? fmaxf(y, 0.f) : y;      // slot (0, t, o) == i: only read by this thread in the loop above
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    // ---- publish this rank's columns into every rank's copy of ys
+    if (sync & SYNC_BEFORE) cl_sync(cl);
+    for (int r = 0; r < cl.size; ++r) {
+        float* dst = cl_remote(ys, cl, r);
+        for (int i = tid; i < NT * ncol; i += nthr) dst[(i / ncol) * ldy + c_lo + i % ncol] = red[i];
+    }
+    if (sync & SYNC_AFTER) cl_sync(cl);
+    else __syncthreads();       // `red` is reused by the next step
 }
 
 // dst[t][:] = LayerNorm(a[t][:] + (r ? r[t][:] : 0)) over 256 channels, eps 1e-5 (nn.LayerNorm default); one warp per token
@@ -411,13 +427,15 @@ __device__ void tok_small_attention(const float* q, const float* k, const float*
 }
 
 // Token -> image attention: 6 queries (smem, [6][128]) against the T keys of this image (fp32 [T,128] in HBM).
-// A warp reads one whole key row per load (lane = 4 channels, 4 lanes per head: 512 contiguous bytes), the 16-channel
-// dot products are finished with two shuffles, and every lane carries an online-softmax state (m, l, 4 channels of the
-// output) for the 6 tokens of its head.  The 16 warps take interleaved keys; their states are merged through `red`
-// ([16][6][160] floats) in warp order, so the result does not depend on scheduling.
+// Rank r of the cluster takes the keys [r T / size, (r+1) T / size).  A warp reads one whole key row per load (lane = 4
+// channels, 4 lanes per head: 512 contiguous bytes), the 16-channel dot products are finished with two shuffles, and every
+// lane carries an online-softmax state (m, l, 4 channels of the output) for the 6 tokens of its head.  The 16 warps'
+// states are merged through `red` ([16][6][192] floats) in warp order, the ranks' merged states through `part`
+// ([size][6][192] in every CTA) in rank order, so the result does not depend on scheduling.
 __device__ void tok_image_attention(const float* qs, const float* __restrict__ kimg, const float* __restrict__ vimg,
-                                    int T, float* out, float* red) {
+                                    int T, float* out, float* red, float* part, const Cl& cl) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    constexpr int STRIDE = DI + 32 + 32;
     float4 q[NTOK], acc[NTOK];
     float m[NTOK], l[NTOK];
 #pragma unroll
@@ -430,8 +448,9 @@ __device__ void tok_image_attention(const float* qs, const float* __restrict__ k
     }
     const float4* kp = reinterpret_cast<const float4*>(kimg) + lane;
     const float4* vp = reinterpret_cast<const float4*>(vimg) + lane;
-    for (int key = warp; key < T; key += 2 * nw) {
-        const bool two = key + nw < T;
+    const int k_lo = (T / cl.size) * cl.rank, k_hi = cl.rank == cl.size - 1 ? T : k_lo + T / cl.size;
+    for (int key = k_lo + warp; key < k_hi; key += 2 * nw) {
+        const bool two = key + nw < k_hi;
         const float4 k0 = __ldg(kp + static_cast<long long>(key) * (DI / 4));
         const float4 v0 = __ldg(vp + static_cast<long long>(key) * (DI / 4));
         const float4 k1 = two ? __ldg(kp + static_cast<long long>(key + nw) * (DI / 4)) : k0;
@@ -455,8 +474,6 @@ __device__ void tok_image_attention(const float* qs, const float* __restrict__ k
             m[t] = mn;
         }
     }
-    // merge the warps: red[warp][t] = {acc (128 floats), m (32: one per lane), l-less: l is folded below}
-    constexpr int STRIDE = DI + 32 + 32;
 #pragma unroll
     for (int t = 0; t < NTOK; ++t) {
         float* r = red + (warp * NTOK + t) * STRIDE;
@@ -465,22 +482,42 @@ __device__ void tok_image_attention(const float* qs, const float* __restrict__ k
         r[DI + 32 + lane] = l[t];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NTOK * 32; i += blockDim.x) {
-        const int t = i >> 5, ln = i & 31;
-        float mm = -INFINITY;
-        for (int w = 0; w < nw; ++w) mm = fmaxf(mm, red[(w * NTOK + t) * STRIDE + DI + ln]);
-        float lt = 0.f;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int w = 0; w < nw; ++w) {
-            const float* r = red + (w * NTOK + t) * STRIDE;
+    // merge `n` states laid out [n][NTOK][STRIDE] at `src` for (token t, lane ln); returns the un-normalised state
+    auto merge = [&](const float* src, int n, int t, int ln, float4& a, float& mm, float& lt) {
+        mm = -INFINITY;
+        for (int w = 0; w < n; ++w) mm = fmaxf(mm, src[(w * NTOK + t) * STRIDE + DI + ln]);
+        lt = 0.f;
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < n; ++w) {
+            const float* r = src + (w * NTOK + t) * STRIDE;
             const float mw = r[DI + ln];
             const float c = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
             lt = fmaf(r[DI + 32 + ln], c, lt);
             const float4 av = *reinterpret_cast<const float4*>(r + 4 * ln);
             a.x = fmaf(av.x, c, a.x); a.y = fmaf(av.y, c, a.y); a.z = fmaf(av.z, c, a.z); a.w = fmaf(av.w, c, a.w);
         }
+    };
+    float4 a[1];
+    float mm = 0.f, lt = 0.f;
+    const bool owner = threadIdx.x < NTOK * 32;      // one thread per (token, lane)
+    const int t = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (owner) merge(red, nw, t, ln, a[0], mm, lt);
+    if (cl.size > 1) {
+        cl_sync(cl);                                  // every rank is done reading `part` (previous use) and `out`
+        if (owner) {
+            for (int r = 0; r < cl.size; ++r) {
+                float* dst = cl_remote(part, cl, r) + (cl.rank * NTOK + t) * STRIDE;
+                *reinterpret_cast<float4*>(dst + 4 * ln) = a[0];
+                dst[DI + ln] = mm;
+                dst[DI + 32 + ln] = lt;
+            }
+        }
+        cl_sync(cl);
+        if (owner) merge(part, cl.size, t, ln, a[0], mm, lt);
+    }
+    if (owner) {
         const float inv = 1.f / lt;
-        *reinterpret_cast<float4*>(out + t * DI + 4 * ln) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+        *reinterpret_cast<float4*>(out + t * DI + 4 * ln) = make_float4(a[0].x * inv, a[0].y * inv, a[0].z * inv, a[0].w * inv);
     }
     __syncthreads();
 }
@@ -495,76 +532,77 @@ constexpr int SM_T3 = SM_T2 + MAXC * DD;
 constexpr int SM_T4 = SM_T3 + MAXC * DD;
 constexpr int SM_CND = SM_T4 + MAXC * DD;     // prompt tokens    [8][256]
 constexpr int SM_CN2 = SM_CND + MAXC * DD;    // 2 * prompt       [8][256]  (k = cond + cond, transformer_maskdecoder_edge.py:188)
-constexpr int SM_RED = SM_CN2 + MAXC * DD;    // split-K partials ([8][6][256] at most) / attention merge [16][6][192]
-constexpr int SM_HID = SM_RED + 16 * NTOK * 192;   // MLP hidden       [6][mlp_dim]
+constexpr int SM_RED = SM_CN2 + MAXC * DD;    // split-K partials / attention merge of the 16 warps [16][6][192]
+constexpr int SM_HID = SM_RED + RED_FLOATS;   // MLP hidden [6][mlp_dim]; the ranks' attention states [8][6][192] before that
+constexpr int HID_MIN_FLOATS = 8 * NTOK * 192;
 
-// One TwoWayAttentionBlock, token side (transformer_maskdecoder_edge.py:161-199), for image blockIdx.x; then the key /
-// value projections that the image side of the same block consumes (:201-212).
+// One TwoWayAttentionBlock, token side (transformer_maskdecoder_edge.py:161-199), for image blockIdx.x / cluster size; then
+// the key / value projections that the image side of the same block consumes (:201-212).
 __global__ void __launch_bounds__(TOK_THREADS) dec_token_layer_kernel(
     LayerW w, int first, int nc, int T, float eps, const float* __restrict__ tokens0, const float* __restrict__ cond,
     float* __restrict__ qbuf, const float* __restrict__ kimg, const float* __restrict__ vimg, float* __restrict__ kc,
     float* __restrict__ vc, float* __restrict__ ktok, float* __restrict__ vtok) {
     extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x;
+    const Cl cl{static_cast<int>(cg::this_cluster().block_rank()), static_cast<int>(cg::this_cluster().num_blocks())};
+    const int b = blockIdx.x / cl.size;
     float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3,
           *T4 = sm + SM_T4, *CND = sm + SM_CND, *CN2 = sm + SM_CN2, *HID = sm + SM_HID, *RED = sm + SM_RED;
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
         PE[i] = tokens0[i];
         Q[i] = first ? tokens0[i] : qbuf[static_cast<long long>(b) * NTOK * DD + i];
     }
-    for (int i = threadIdx.x; i < nc * DD; i += blockDim.x) {
-        const float c = cond[static_cast<long long>(b) * nc * DD + i];
+    for (int i = threadIdx.x; i < MAXC * DD; i += blockDim.x) {
+        const float c = i < nc * DD ? cond[static_cast<long long>(b) * nc * DD + i] : 0.f;
         CND[i] = c;
         CN2[i] = c + c;
     }
     __syncthreads();
+    const float* kb_ = kimg + static_cast<long long>(b) * T * DI;
+    const float* vb_ = vimg + static_cast<long long>(b) * T * DI;
     // ---- self attention (:163-170); the first layer skips the positional term and the shortcut
     tok_axpy(X, Q, PE, first ? 0.f : 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.self_attn.qw, w.self_attn.qb, X, DD, DD, T1, DD, DD, false, RED);
-    tok_linear<NTOK>(w.self_attn.kw, w.self_attn.kb, X, DD, DD, T2, DD, DD, false, RED);
-    tok_linear<NTOK>(w.self_attn.vw, w.self_attn.vb, Q, DD, DD, T3, DD, DD, false, RED);
+    tok_linear<NTOK>(w.self_attn.qw, w.self_attn.qb, X, DD, DD, T1, DD, DD, false, RED, cl, SYNC_BEFORE);
+    tok_linear<NTOK>(w.self_attn.kw, w.self_attn.kb, X, DD, DD, T2, DD, DD, false, RED, cl, 0);
+    tok_linear<NTOK>(w.self_attn.vw, w.self_attn.vb, Q, DD, DD, T3, DD, DD, false, RED, cl, SYNC_AFTER);
     tok_small_attention(T1, T2, T3, DD, NTOK, NTOK, DD / NH, T4);
-    tok_linear<NTOK>(w.self_attn.ow, w.self_attn.ob, T4, DD, DD, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.self_attn.ow, w.self_attn.ob, T4, DD, DD, T1, DD, DD, false, RED, cl, SYNC_BOTH);
     tok_add_ln(Q, T1, first ? nullptr : Q, w.n1, eps, NTOK);
     // ---- token -> image cross attention (:172-177); kimg = (keys + pe) Wk, vimg = keys Wv come from the GEMMs
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED);
-    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2, RED);
-    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED, cl, SYNC_BOTH);
+    tok_image_attention(T1, kb_, vb_, T, T2, RED, HID, cl);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED, cl, SYNC_BOTH);
     tok_add_ln(Q, Q, T1, w.n2, eps, NTOK);
     // ---- token -> prompt cross attention (:179-192): q = queries + pe, k = cond + cond, v = cond
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2c.qw, w.t2c.qb, X, DD, DD, T1, DI, DI, false, RED);
-    tok_linear<MAXC>(w.t2c.kw, w.t2c.kb, CN2, DD, DD, T2, DI, DI, false, RED);
-    tok_linear<MAXC>(w.t2c.vw, w.t2c.vb, CND, DD, DD, T3, DI, DI, false, RED);
+    tok_linear<NTOK>(w.t2c.qw, w.t2c.qb, X, DD, DD, T1, DI, DI, false, RED, cl, SYNC_BEFORE);
+    tok_linear<MAXC>(w.t2c.kw, w.t2c.kb, CN2, DD, DD, T2, DI, DI, false, RED, cl, 0);
+    tok_linear<MAXC>(w.t2c.vw, w.t2c.vb, CND, DD, DD, T3, DI, DI, false, RED, cl, SYNC_AFTER);
     tok_small_attention(T1, T2, T3, DI, NTOK, nc, DI / NH, T4);
-    tok_linear<NTOK>(w.t2c.ow, w.t2c.ob, T4, DI, DI, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.t2c.ow, w.t2c.ob, T4, DI, DI, T1, DD, DD, false, RED, cl, SYNC_BOTH);
     tok_add_ln(Q, Q, T1, w.n2c, eps, NTOK);
     // ---- MLP (:194-197), ReLU
-    tok_linear<NTOK>(w.l1w, w.l1b, Q, DD, DD, HID, w.mlp_dim, w.mlp_dim, true, RED);
-    tok_linear<NTOK>(w.l2w, w.l2b, HID, w.mlp_dim, w.mlp_dim, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.l1w, w.l1b, Q, DD, DD, HID, w.mlp_dim, w.mlp_dim, true, RED, cl, SYNC_BOTH);
+    tok_linear<NTOK>(w.l2w, w.l2b, HID, w.mlp_dim, w.mlp_dim, T1, DD, DD, false, RED, cl, SYNC_BOTH);
     tok_add_ln(Q, Q, T1, w.n3, eps, NTOK);
-    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) qbuf[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
     // ---- keys / values of the two image-side attentions of this block (:201-212)
-    tok_linear<MAXC>(w.i2c.kw, w.i2c.kb, CN2, DD, DD, T1, DI, DI, false, RED);
-    tok_linear<MAXC>(w.i2c.vw, w.i2c.vb, CND, DD, DD, T2, DI, DI, false, RED);
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.i2t.kw, w.i2t.kb, X, DD, DD, T3, DI, DI, false, RED);
-    tok_linear<NTOK>(w.i2t.vw, w.i2t.vb, Q, DD, DD, T4, DI, DI, false, RED);
-    for (int i = threadIdx.x; i < nc * DI; i += blockDim.x) {
-        kc[static_cast<long long>(b) * nc * DI + i] = T1[i];
-        vc[static_cast<long long>(b) * nc * DI + i] = T2[i];
+    tok_linear<MAXC>(w.i2c.kw, w.i2c.kb, CN2, DD, DD, T1, DI, DI, false, RED, cl, SYNC_BEFORE);
+    tok_linear<MAXC>(w.i2c.vw, w.i2c.vb, CND, DD, DD, T2, DI, DI, false, RED, cl, 0);
+    tok_linear<NTOK>(w.i2t.kw, w.i2t.kb, X, DD, DD, T3, DI, DI, false, RED, cl, 0);
+    tok_linear<NTOK>(w.i2t.vw, w.i2t.vb, Q, DD, DD, T4, DI, DI, false, RED, cl, SYNC_AFTER);
+    if (cl.rank == 0) {
+        for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) qbuf[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
+        for (int i = threadIdx.x; i < nc * DI; i += blockDim.x) {
+            kc[static_cast<long long>(b) * nc * DI + i] = T1[i];
+            vc[static_cast<long long>(b) * nc * DI + i] = T2[i];
+        }
+        for (int i = threadIdx.x; i < NTOK * DI; i += blockDim.x) {
+            ktok[static_cast<long long>(b) * NTOK * DI + i] = T3[i];
+            vtok[static_cast<long long>(b) * NTOK * DI + i] = T4[i];
+        }
     }
-    for (int i = threadIdx.x; i < NTOK * DI; i += blockDim.x) {
-        ktok[static_cast<long long>(b) * NTOK * DI + i] = T3[i];
-        vtok[static_cast<long long>(b) * NTOK * DI + i] = T4[i];
-    }
-}
-
-__device__ void tok_mlp3(const Mlp3W& w, const float* x, int out_dim, float* t1, float* t2, float* y, float* RED) {
-    tok_linear<1>(w.w0, w.b0, x, DD, DD, t1, DD, DD, true, RED);
-    tok_linear<1>(w.w1, w.b1, t1, DD, DD, t2, DD, DD, true, RED);
-    tok_linear<1>(w.w2, w.b2, t2, DD, DD, y, out_dim, out_dim, false, RED);
+    cl_sync(cl);      // no CTA may exit while a peer can still write into its shared memory
 }
 
 // final_attn_token_to_image + norm_final_attn (transformer_maskdecoder_edge.py:98-109), then the hyper-network MLPs,
@@ -577,25 +615,44 @@ __global__ void __launch_bounds__(TOK_THREADS) dec_token_final_kernel(FinalW w, 
                                                                       float* __restrict__ hs, float* __restrict__ hyper,
                                                                       float* __restrict__ iou) {
     extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x;
+    const Cl cl{static_cast<int>(cg::this_cluster().block_rank()), static_cast<int>(cg::this_cluster().num_blocks())};
+    const int b = blockIdx.x / cl.size;
     float *Q = sm + SM_Q, *PE = sm + SM_PE, *X = sm + SM_X, *T1 = sm + SM_T1, *T2 = sm + SM_T2, *T3 = sm + SM_T3,
-          *RED = sm + SM_RED;
+          *RED = sm + SM_RED, *HID = sm + SM_HID;
     for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) {
         PE[i] = tokens0[i];
         Q[i] = qbuf[static_cast<long long>(b) * NTOK * DD + i];
     }
     __syncthreads();
     tok_axpy(X, Q, PE, 1.f, NTOK * DD);
-    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED);
-    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2, RED);
-    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED);
+    tok_linear<NTOK>(w.t2i.qw, w.t2i.qb, X, DD, DD, T1, DI, DI, false, RED, cl, SYNC_BOTH);
+    tok_image_attention(T1, kimg + static_cast<long long>(b) * T * DI, vimg + static_cast<long long>(b) * T * DI, T, T2, RED, HID, cl);
+    tok_linear<NTOK>(w.t2i.ow, w.t2i.ob, T2, DI, DI, T1, DD, DD, false, RED, cl, SYNC_BOTH);
     tok_add_ln(Q, Q, T1, w.nf, eps, NTOK);
-    for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) hs[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
-    for (int i = 0; i <= NMASK; ++i)
-        tok_mlp3(w.hyper[i], Q + (1 + i) * DD, DE, T1, T2, T3 + i * DE, RED);
-    tok_mlp3(w.iou, Q, NMASK, T1, T2, T3 + (NMASK + 1) * DE, RED);
-    for (int i = threadIdx.x; i < (NMASK + 1) * DE; i += blockDim.x) hyper[static_cast<long long>(b) * (NMASK + 1) * DE + i] = T3[i];
-    for (int i = threadIdx.x; i < NMASK; i += blockDim.x) iou[b * NMASK + i] = T3[(NMASK + 1) * DE + i];
+    if (cl.rank == 0)
+        for (int i = threadIdx.x; i < NTOK * DD; i += blockDim.x) hs[static_cast<long long>(b) * NTOK * DD + i] = Q[i];
+    // six independent 3-layer MLPs, layer by layer: hyper-networks 0..3 on the mask tokens, edge_mlp on the edge token,
+    // the IoU head on the IoU token
+    constexpr int NMLP = NMASK + 2;
+    for (int i = 0; i < NMLP; ++i) {
+        const Mlp3W& m = i <= NMASK ? w.hyper[i] : w.iou;
+        const float* x = i <= NMASK ? Q + (1 + i) * DD : Q;
+        tok_linear<1>(m.w0, m.b0, x, DD, DD, T1 + i * DD, DD, DD, true, RED, cl, (i == 0 ? SYNC_BEFORE : 0) | (i == NMLP - 1 ? SYNC_AFTER : 0));
+    }
+    for (int i = 0; i < NMLP; ++i) {
+        const Mlp3W& m = i <= NMASK ? w.hyper[i] : w.iou;
+        tok_linear<1>(m.w1, m.b1, T1 + i * DD, DD, DD, T2 + i * DD, DD, DD, true, RED, cl, (i == 0 ? SYNC_BEFORE : 0) | (i == NMLP - 1 ? SYNC_AFTER : 0));
+    }
+    for (int i = 0; i < NMLP; ++i) {
+        const Mlp3W& m = i <= NMASK ? w.hyper[i] : w.iou;
+        const int od = i <= NMASK ? DE : NMASK;
+        tok_linear<1>(m.w2, m.b2, T2 + i * DD, DD, DD, T3 + i * DE, od, od, false, RED, cl, (i == 0 ? SYNC_BEFORE : 0) | (i == NMLP - 1 ? SYNC_AFTER : 0));
+    }
+    if (cl.rank == 0) {
+        for (int i = threadIdx.x; i < (NMASK + 1) * DE; i += blockDim.x) hyper[static_cast<long long>(b) * (NMASK + 1) * DE + i] = T3[i];
+        for (int i = threadIdx.x; i < NMASK; i += blockDim.x) iou[b * NMASK + i] = T3[(NMASK + 1) * DE + i];
+    }
+    cl_sync(cl);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -844,14 +901,40 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     auto F32 = [&](long long off) { return reinterpret_cast<float*>(base + off); };
     auto PTR = [&](long long off) { return static_cast<void*>(base + off); };
     DecFwd f{dec, stream};
-    const size_t tok_smem = static_cast<size_t>(SM_HID + NTOK * c.mlp_dim) * sizeof(float);
+    const int hid_floats = NTOK * c.mlp_dim > HID_MIN_FLOATS ? NTOK * c.mlp_dim : HID_MIN_FLOATS;
+    const size_t tok_smem = static_cast<size_t>(SM_HID + hid_floats) * sizeof(float);
+    if (tok_smem > 220 * 1024) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: mlp_dim %d needs too much shared memory", c.mlp_dim);
     static bool attr_done = false;
     if (!attr_done) {
-        CVLM_CUDA(cudaFuncSetAttribute(dec_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CVLM_CUDA(cudaFuncSetAttribute(dec_token_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CVLM_CUDA(cudaFuncSetAttribute(dec_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CVLM_CUDA(cudaFuncSetAttribute(dec_token_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
-    if (tok_smem > 200 * 1024) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: mlp_dim %d needs too much shared memory", c.mlp_dim);
+    // CTAs per image on the token side: as many as keep the whole batch in one wave (CVLM_DEC_CLUSTER overrides: tests)
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int csize = 8;
+    while (csize > 1 && batch * csize > sms) csize >>= 1;
+    if (const char* e = getenv("CVLM_DEC_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) csize = v;
+    }
+    cudaLaunchAttribute tok_attr[1];
+    tok_attr[0].id = cudaLaunchAttributeClusterDimension;
+    tok_attr[0].val.clusterDim.x = csize;
+    tok_attr[0].val.clusterDim.y = 1;
+    tok_attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t tok_cfg = {};
+    tok_cfg.gridDim = dim3(batch * csize);
+    tok_cfg.blockDim = dim3(TOK_THREADS);
+    tok_cfg.dynamicSmemBytes = tok_smem;
+    tok_cfg.stream = stream;
+    tok_cfg.attrs = tok_attr;
+    tok_cfg.numAttrs = 1;
 
     // tokens: [iou_token; mask_tokens; edge_token] (mask_decoder_edge.py:157), packed by the host side
     const float* tokens0 = nullptr;
@@ -919,10 +1002,9 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wk, DI, lw.t2i.kb, nullptr, PTR(ws.kimg)));
         CVLM_TRY(f.gemm(PTR(ws.kb), M, DD, wv, DI, lw.t2i.vb, nullptr, PTR(ws.vimg)));
         ++f.launches;
-        dec_token_layer_kernel<<<batch, TOK_THREADS, tok_smem, stream>>>(lw, i == 0 ? 1 : 0, nc, T, c.ln_eps, tokens0, sparse,
-                                                                          F32(ws.qbuf), F32(ws.kimg), F32(ws.vimg), F32(ws.kc),
-                                                                          F32(ws.vc), F32(ws.ktok), F32(ws.vtok));
-        CVLM_CUDA(cudaGetLastError());
+        CVLM_CUDA(cudaLaunchKernelEx(&tok_cfg, dec_token_layer_kernel, lw, i == 0 ? 1 : 0, nc, T, c.ln_eps, tokens0, sparse,
+                                     F32(ws.qbuf), static_cast<const float*>(F32(ws.kimg)), static_cast<const float*>(F32(ws.vimg)),
+                                     F32(ws.kc), F32(ws.vc), F32(ws.ktok), F32(ws.vtok)));
         // image -> prompt attention, norm4_cond (:201-206)
         CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wqc, DI, lw.i2c.qb, nullptr, PTR(ws.qi)));
         ++f.launches;
@@ -957,10 +1039,9 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         CVLM_TRY(f.gemm(PTR(ws.kpb), M, DD, wk, DI, fw.t2i.kb, nullptr, PTR(ws.kimg)));
         CVLM_TRY(f.gemm(PTR(ws.kb), M, DD, wv, DI, fw.t2i.vb, nullptr, PTR(ws.vimg)));
         ++f.launches;
-        dec_token_final_kernel<<<batch, TOK_THREADS, tok_smem, stream>>>(fw, T, c.ln_eps, tokens0, F32(ws.qbuf), F32(ws.kimg),
-                                                                          F32(ws.vimg), hs_out ? hs_out : F32(ws.hs),
-                                                                          F32(ws.hyper), iou);
-        CVLM_CUDA(cudaGetLastError());
+        CVLM_CUDA(cudaLaunchKernelEx(&tok_cfg, dec_token_final_kernel, fw, T, c.ln_eps, tokens0, static_cast<const float*>(F32(ws.qbuf)),
+                                     static_cast<const float*>(F32(ws.kimg)), static_cast<const float*>(F32(ws.vimg)),
+                                     hs_out ? hs_out : F32(ws.hs), F32(ws.hyper), iou));
     }
     // ---- output_upscaling(keys) (mask_decoder_edge.py:165-166, :53-59)
     {

@@ -149,3 +149,23 @@ def test_decoder_rejects_bad_shapes():
         with pytest.raises(Exception, match="multiple of 8"):
             dec(torch.zeros(1, 256, 12, 12).cuda(), [], mdo.dense_pe(sd, 12).cuda(), torch.zeros(1, 2, 256).cuda(),
                 torch.zeros(1, 256, 12, 12).cuda(), False)
+
+
+@pytest.mark.parametrize("csize", [1, 2, 4, 8])
+def test_decoder_token_cluster_sizes(csize, monkeypatch):
+    # the token side runs one CTA cluster per image; every cluster size must give the same answer (up to the fp32
+    # summation order of the K split) and match the oracle
+    monkeypatch.setenv("CVLM_DEC_CLUSTER", str(csize))
+    dec, sd = build(1)
+    gen = torch.Generator().manual_seed(21)
+    emb = torch.randn(2, 256, 16, 16, generator=gen)
+    sparse = torch.randn(2, 3, 256, generator=gen)
+    masks, edge, iou = run(dec, sd, emb, sparse)
+    hs = dec.last_hs.clone()
+    for b in range(2):
+        want = mdo.decode_all(sd, emb[b:b + 1], sparse[b:b + 1])
+        assert rel_l2(hs[b:b + 1].cpu(), want["hs"]) < 3e-3
+        assert rel_l2(masks[b:b + 1].cpu(), want["masks"][:, 0:1]) < TOL
+        assert float((iou[b:b + 1].cpu() - want["iou"][:, 0:1]).abs().max()) < 1e-3
+    again = run(dec, sd, emb, sparse)
+    assert torch.equal(again[0], masks) and torch.equal(dec.last_hs, hs)      # deterministic run to run
