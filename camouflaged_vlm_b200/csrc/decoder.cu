@@ -5,10 +5,11 @@
 //
 // Split of the work
 //   image side  (4096 keys x 256 per image, and the 128^2 / 256^2 up-scaling maps): every projection, both transposed
-//               convolutions (k2 s2: four GEMM column groups per input pixel) and both 3x3 convolutions (im2col) run on
-//               the tcgen05 GEMM (gemm_tcgen05.cu) with bf16 operands and fp32 accumulation; `keys` stays fp32.
-//   token side  (6 output tokens + the prompt tokens per image): one CTA per image runs a whole transformer layer in
-//               fp32 (self attention, token->image attention over the 4096 keys, token->prompt attention, MLP, and the
+//               convolutions (k2 s2: four GEMM column groups per input pixel) and both 3x3 convolutions (implicit GEMM,
+//               no im2col) run on the tcgen05 GEMM (gemm_tcgen05.cu) with bf16 operands and fp32 accumulation; `keys`
+//               stays fp32.
+//   token side  (6 output tokens + the prompt tokens per image): one CTA cluster per image runs a whole transformer layer
+//               in fp32 (self attention, token->image attention over the 4096 keys, token->prompt attention, MLP, and the
 //               key / value projections the image side needs next).
 //
 // Data layout in HBM for a chunk of B images (T = g*g, M = B*T; P1 = 4M, P2 = 16M pixels of the up-scaled maps):
@@ -123,61 +124,71 @@ __global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ out_b16,
                                                           __nv_bfloat16* __restrict__ out_pos_b16, long long rows,
                                                           int pad_pitch) {
-    // a row is covered by C/4 lanes holding 4 consecutive channels each: one warp normalises 128/C rows
+    // a row is covered by C/4 lanes holding 4 consecutive channels each: one warp normalises 128/C rows at a time, and
+    // RPT such groups of rows per thread so that enough loads are in flight for the narrow maps
     constexpr int LPR = C / 4;              // lanes per row: 64 (C = 256, two passes of the warp) or 16 (C = 64)
     constexpr int RPW = LPR >= 32 ? 1 : 32 / LPR;
     constexpr int PASS = LPR >= 32 ? LPR / 32 : 1;
+    constexpr int RPT = C >= 128 ? 1 : 2;
     const int lane = threadIdx.x & 31;
-    const long long row = (static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * RPW + (RPW > 1 ? lane / LPR : 0);
-    const bool live = row < rows;
     const int c0 = (RPW > 1 ? lane % LPR : lane) * 4;
-    float4 v[PASS];
-    float s = 0.f;
+    long long row[RPT];
+    float4 v[RPT][PASS];
 #pragma unroll
-    for (int j = 0; j < PASS; ++j) {
-        v[j] = live ? *reinterpret_cast<const float4*>(x + row * C + c0 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    for (int r = 0; r < RPT; ++r) {
+        row[r] = ((static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * RPT + r) * RPW + (RPW > 1 ? lane / LPR : 0);
+#pragma unroll
+        for (int j = 0; j < PASS; ++j)
+            v[r][j] = row[r] < rows ? *reinterpret_cast<const float4*>(x + row[r] * C + c0 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.f / C);
-    float q = 0.f;
+    for (int r = 0; r < RPT; ++r) {
+        float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < PASS; ++j) {
-        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-        q += fmaf(v[j].x, v[j].x, v[j].y * v[j].y) + fmaf(v[j].z, v[j].z, v[j].w * v[j].w);
-    }
+        for (int j = 0; j < PASS; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
 #pragma unroll
-    for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.f / sqrtf(q * (1.f / C) + eps);
-    if (!live) return;
-    // padded raster maps (pad_pitch > 0): the border rows feed the next implicit convolution and must stay zero
-    bool border = false;
-    if (pad_pitch > 0) {
-        const int pr = static_cast<int>(row % (static_cast<long long>(pad_pitch) * pad_pitch));
-        const int py = pr / pad_pitch, px = pr % pad_pitch;
-        border = py == 0 || py == pad_pitch - 1 || px == 0 || px == pad_pitch - 1;
-    }
+        for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.f / C);
+        float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < PASS; ++j) {
-        const int c = c0 + 128 * j;
-        if (border) {
-            if (out_b16) *reinterpret_cast<uint2*>(out_b16 + row * C + c) = make_uint2(0u, 0u);
-            continue;
+        for (int j = 0; j < PASS; ++j) {
+            v[r][j].x -= mean; v[r][j].y -= mean; v[r][j].z -= mean; v[r][j].w -= mean;
+            q += fmaf(v[r][j].x, v[r][j].x, v[r][j].y * v[r][j].y) + fmaf(v[r][j].z, v[r][j].z, v[r][j].w * v[r][j].w);
         }
-        const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
-        float4 y = make_float4(fmaf(v[j].x * rstd, gm.x, bt.x), fmaf(v[j].y * rstd, gm.y, bt.y),
-                               fmaf(v[j].z * rstd, gm.z, bt.z), fmaf(v[j].w * rstd, gm.w, bt.w));
-        if (gelu) y = make_float4(gelu_exact(y.x), gelu_exact(y.y), gelu_exact(y.z), gelu_exact(y.w));
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
-        if (out_b16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
-            *reinterpret_cast<uint2*>(out_b16 + row * C + c) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+#pragma unroll
+        for (int o = (LPR >= 32 ? 16 : LPR / 2); o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = 1.f / sqrtf(q * (1.f / C) + eps);
+        if (row[r] >= rows) continue;
+        // padded raster maps (pad_pitch > 0): the border rows feed the next implicit convolution and must stay zero
+        bool border = false;
+        if (pad_pitch > 0) {
+            const unsigned pp = static_cast<unsigned>(pad_pitch) * pad_pitch;
+            const unsigned pr = static_cast<unsigned>(row[r]) % pp;      // rows < 2^31 (checked by the host)
+            const unsigned py = pr / pad_pitch, px = pr % pad_pitch;
+            border = py == 0 || py == static_cast<unsigned>(pad_pitch) - 1 || px == 0 || px == static_cast<unsigned>(pad_pitch) - 1;
         }
-        if (out_pos_b16) {
-            const float4 p = *reinterpret_cast<const float4*>(pos + (row % T) * C + c);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(y.x + p.x, y.y + p.y), hi = __floats2bfloat162_rn(y.z + p.z, y.w + p.w);
-            *reinterpret_cast<uint2*>(out_pos_b16 + row * C + c) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+#pragma unroll
+        for (int j = 0; j < PASS; ++j) {
+            const int c = c0 + 128 * j;
+            const long long off = row[r] * C + c;
+            if (border) {
+                if (out_b16) *reinterpret_cast<uint2*>(out_b16 + off) = make_uint2(0u, 0u);
+                continue;
+            }
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+            float4 y = make_float4(fmaf(v[r][j].x * rstd, gm.x, bt.x), fmaf(v[r][j].y * rstd, gm.y, bt.y),
+                                   fmaf(v[r][j].z * rstd, gm.z, bt.z), fmaf(v[r][j].w * rstd, gm.w, bt.w));
+            if (gelu) y = make_float4(gelu_exact(y.x), gelu_exact(y.y), gelu_exact(y.z), gelu_exact(y.w));
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = y;
+            if (out_b16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+                *reinterpret_cast<uint2*>(out_b16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
+            if (out_pos_b16) {
+                const float4 p = *reinterpret_cast<const float4*>(pos + (row[r] % T) * C + c);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(y.x + p.x, y.y + p.y), hi = __floats2bfloat162_rn(y.z + p.z, y.w + p.w);
+                *reinterpret_cast<uint2*>(out_pos_b16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
         }
     }
 }
@@ -873,7 +884,7 @@ template <int C>
 int ln_rows(DecFwd& f, const float* x, const float* gamma, const float* beta, float eps, int gelu, const float* pos, int T,
             float* out_f32, void* out_b16, void* out_pos_b16, long long rows, int pad_pitch = 0) {
     ++f.launches;
-    constexpr int rows_per_block = 8 * (C >= 128 ? 1 : 128 / C);
+    constexpr int rows_per_block = 8 * (C >= 128 ? 1 : 2 * (128 / C));
     dec_ln_rows_kernel<C><<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), 256, 0, f.stream>>>(
         x, gamma, beta, eps, gelu, pos, T, out_f32, static_cast<__nv_bfloat16*>(out_b16),
         static_cast<__nv_bfloat16*>(out_pos_b16), rows, pad_pitch);

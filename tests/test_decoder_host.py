@@ -105,3 +105,17 @@ def test_decoder_handle_workspace_and_config_validation():
         h2 = C.c_void_p()
         assert lib.cvlm_decoder_create(C.byref(cfg(**bad)), C.byref(h2)) == -3, bad
         assert lib.cvlm_last_error()
+
+
+def test_decoder_accepts_the_reference_transformer_instance():
+    from oracle.ref_import import reference_available
+    if not reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle.ref_import import load_reference_decoder_modules
+    _, tr = load_reference_decoder_modules()
+    dec = md.MaskDecoder(num_multimask_outputs=3, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                         transformer=tr.TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8))
+    assert set(dec.state_dict()) == set(mdo.decoder_param_shapes())
+    packed = md.pack_decoder_weights(dict(dec.state_dict()), 2, torch.device("cpu"))
+    assert packed["transformer.layers.1.mlp.lin1.weight.t"].shape == (256, 2048)
+    assert packed["transformer.final_attn_token_to_image.k_proj.weight.bf16"].dtype == torch.bfloat16
