@@ -200,23 +200,23 @@ __global__ void __launch_bounds__(256) dec_ln_rows_kernel(const float* __restric
 __global__ void __launch_bounds__(256) dec_few_key_attn_kernel(const float* __restrict__ q, const float* __restrict__ kt,
                                                                const float* __restrict__ vt, int nk,
                                                                __nv_bfloat16* __restrict__ out, int T) {
-    __shared__ float ks[MAXC][DI], vs[MAXC][DI];
+    // keys / values of this image in shared memory as [key][quarter of the head][head] float4: the 8 heads of a row sit
+    // in consecutive lanes, so every 128-bit shared load of a quarter-warp is conflict free
+    __shared__ float4 ks[MAXC][4][NH], vs[MAXC][4][NH];
     const long long row0 = static_cast<long long>(blockIdx.x) * 32;
     const int b = static_cast<int>(row0 / T);
-    for (int i = threadIdx.x; i < nk * DI; i += 256) {
-        ks[i / DI][i % DI] = kt[static_cast<long long>(b) * nk * DI + i];
-        vs[i / DI][i % DI] = vt[static_cast<long long>(b) * nk * DI + i];
+    for (int i = threadIdx.x; i < nk * (DI / 4); i += 256) {
+        const int j = i / (DI / 4), c4 = i % (DI / 4);          // float4 c4 of key j: head c4 / 4, quarter c4 % 4
+        ks[j][c4 & 3][c4 >> 2] = reinterpret_cast<const float4*>(kt + static_cast<long long>(b) * nk * DI)[i];
+        vs[j][c4 & 3][c4 >> 2] = reinterpret_cast<const float4*>(vt + static_cast<long long>(b) * nk * DI)[i];
     }
     __syncthreads();
     const int h = threadIdx.x & 7;
     const long long row = row0 + (threadIdx.x >> 3);
-    float qv[16];
+    float4 qv[4];
     const float4* qp = reinterpret_cast<const float4*>(q + row * DI + h * 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 t = qp[i];
-        qv[4 * i] = t.x; qv[4 * i + 1] = t.y; qv[4 * i + 2] = t.z; qv[4 * i + 3] = t.w;
-    }
+    for (int i = 0; i < 4; ++i) qv[i] = qp[i];
     float lg[MAXC], mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXC; ++j) {
@@ -224,27 +224,38 @@ __global__ void __launch_bounds__(256) dec_few_key_attn_kernel(const float* __re
         if (j < nk) {
             float s = 0.f;
 #pragma unroll
-            for (int d = 0; d < 16; ++d) s = fmaf(qv[d], ks[j][h * 16 + d], s);
+            for (int i = 0; i < 4; ++i) {
+                const float4 kk = ks[j][i][h];
+                s = fmaf(qv[i].x, kk.x, fmaf(qv[i].y, kk.y, fmaf(qv[i].z, kk.z, fmaf(qv[i].w, kk.w, s))));
+            }
             lg[j] = s * 0.25f;     // 1 / sqrt(16)
             mx = fmaxf(mx, lg[j]);
         }
     }
-    float l = 0.f, acc[16];
+    float l = 0.f;
+    float4 acc[4];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < MAXC; ++j) {
         if (j < nk) {
             const float p = expf(lg[j] - mx);
             l += p;
 #pragma unroll
-            for (int d = 0; d < 16; ++d) acc[d] = fmaf(p, vs[j][h * 16 + d], acc[d]);
+            for (int i = 0; i < 4; ++i) {
+                const float4 vv = vs[j][i][h];
+                acc[i].x = fmaf(p, vv.x, acc[i].x); acc[i].y = fmaf(p, vv.y, acc[i].y);
+                acc[i].z = fmaf(p, vv.z, acc[i].z); acc[i].w = fmaf(p, vv.w, acc[i].w);
+            }
         }
     }
     const float inv = 1.f / l;
     __nv_bfloat162 o[8];
 #pragma unroll
-    for (int d = 0; d < 8; ++d) o[d] = __floats2bfloat162_rn(acc[2 * d] * inv, acc[2 * d + 1] * inv);
+    for (int i = 0; i < 4; ++i) {
+        o[2 * i] = __floats2bfloat162_rn(acc[i].x * inv, acc[i].y * inv);
+        o[2 * i + 1] = __floats2bfloat162_rn(acc[i].z * inv, acc[i].w * inv);
+    }
     uint4* op = reinterpret_cast<uint4*>(out + row * DI + h * 16);
     op[0] = *reinterpret_cast<uint4*>(&o[0]);
     op[1] = *reinterpret_cast<uint4*>(&o[4]);
@@ -691,43 +702,52 @@ __global__ void __launch_bounds__(256) dec_pad_raster_kernel(const __nv_bfloat16
 
 // ------------------------------------------------------------------------------------------------------------------
 // masks = hyper[:4] . upscaled, edge = sigmoid(hyper[4] . edge_embedding), masks = masks * edge + masks
-// (mask_decoder_edge.py:176-183).  One thread per output pixel in raster order; `up` and the edge features are in
-// nested order, the output of embedding_maskfeature in padded raster order.
+// (mask_decoder_edge.py:176-183).  `up` and the edge features are in nested order, the output of
+// embedding_maskfeature in padded raster order, the outputs in raster order.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_masks_kernel(const float* __restrict__ up, const float* __restrict__ ee,
                                                         const float* __restrict__ ef, const float* __restrict__ hyper,
                                                         float* __restrict__ masks, float* __restrict__ edge, int g) {
-    __shared__ float hy[(NMASK + 1) * DE];
+    // 8 lanes per pixel (one float4 of the 32 channels each: a warp reads four whole 128-byte rows per load), pixels
+    // walked in nested order, the five 32-term dot products finished with three shuffles
+    __shared__ float4 hy[NMASK + 1][DE / 4];
     const int b = blockIdx.y, S = 4 * g, P2 = S * S, pitch = S + 2;
-    if (threadIdx.x < (NMASK + 1) * DE) hy[threadIdx.x] = hyper[b * (NMASK + 1) * DE + threadIdx.x];
+    if (threadIdx.x < (NMASK + 1) * DE / 4)
+        hy[threadIdx.x / (DE / 4)][threadIdx.x % (DE / 4)] = reinterpret_cast<const float4*>(hyper + b * (NMASK + 1) * DE)[threadIdx.x];
     __syncthreads();
-    const int pix = blockIdx.x * 256 + threadIdx.x;
-    if (pix >= P2) return;
-    const int Y = pix / S, X = pix % S;
-    const long long row = static_cast<long long>(b) * P2 + raster_to_nested(Y, X, g);                 // nested maps
+    const int n = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;      // P2 is a multiple of 32
+    const int p = n >> 4, s1 = (n >> 2) & 3, s2 = n & 3;
+    const int Y = (p / g) * 4 + (s1 >> 1) * 2 + (s2 >> 1), X = (p % g) * 4 + (s1 & 1) * 2 + (s2 & 1);
+    const long long row = static_cast<long long>(b) * P2 + n;                                          // nested maps
     const long long prow = static_cast<long long>(b) * pitch * pitch + (Y + 1) * pitch + (X + 1);     // padded raster map
-    float u[DE], e[DE];
-    const float4* upp = reinterpret_cast<const float4*>(up + row * DE);
-    const float4* eep = reinterpret_cast<const float4*>(ee + prow * DE);
-    const float4* efp = reinterpret_cast<const float4*>(ef + row * DE);
-#pragma unroll
-    for (int i = 0; i < DE / 4; ++i) {
-        const float4 a = upp[i], c = eep[i], f = efp[i];
-        u[4 * i] = a.x; u[4 * i + 1] = a.y; u[4 * i + 2] = a.z; u[4 * i + 3] = a.w;
-        // edge_embedding = embedding_maskfeature(upscaled) + edge features (mask_decoder_edge.py:168)
-        e[4 * i] = c.x + f.x; e[4 * i + 1] = c.y + f.y; e[4 * i + 2] = c.z + f.z; e[4 * i + 3] = c.w + f.w;
-    }
-    float ed = 0.f;
-#pragma unroll
-    for (int d = 0; d < DE; ++d) ed = fmaf(hy[NMASK * DE + d], e[d], ed);
-    ed = 1.f / (1.f + expf(-ed));
-    edge[static_cast<long long>(b) * P2 + pix] = ed;
+    const float4 u = reinterpret_cast<const float4*>(up + row * DE)[sub];
+    const float4 c = reinterpret_cast<const float4*>(ee + prow * DE)[sub];
+    const float4 f = reinterpret_cast<const float4*>(ef + row * DE)[sub];
+    // edge_embedding = embedding_maskfeature(upscaled) + edge features (mask_decoder_edge.py:168)
+    const float4 e = make_float4(c.x + f.x, c.y + f.y, c.z + f.z, c.w + f.w);
+    float d[NMASK + 1];
 #pragma unroll
     for (int i = 0; i < NMASK; ++i) {
-        float m = 0.f;
+        const float4 hv = hy[i][sub];
+        d[i] = fmaf(hv.x, u.x, fmaf(hv.y, u.y, fmaf(hv.z, u.z, hv.w * u.w)));
+    }
+    {
+        const float4 hv = hy[NMASK][sub];
+        d[NMASK] = fmaf(hv.x, e.x, fmaf(hv.y, e.y, fmaf(hv.z, e.z, hv.w * e.w)));
+    }
 #pragma unroll
-        for (int d = 0; d < DE; ++d) m = fmaf(hy[i * DE + d], u[d], m);
-        masks[(static_cast<long long>(b) * NMASK + i) * P2 + pix] = __fadd_rn(__fmul_rn(m, ed), m);
+    for (int i = 0; i <= NMASK; ++i) {
+        d[i] += __shfl_xor_sync(0xffffffffu, d[i], 1);
+        d[i] += __shfl_xor_sync(0xffffffffu, d[i], 2);
+        d[i] += __shfl_xor_sync(0xffffffffu, d[i], 4);
+    }
+    if (sub == 0) {
+        const float ed = 1.f / (1.f + expf(-d[NMASK]));
+        const int pix = Y * S + X;
+        edge[static_cast<long long>(b) * P2 + pix] = ed;
+#pragma unroll
+        for (int i = 0; i < NMASK; ++i)
+            masks[(static_cast<long long>(b) * NMASK + i) * P2 + pix] = __fadd_rn(__fmul_rn(d[i], ed), d[i]);
     }
 }
 
@@ -1092,7 +1112,7 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     }
     // ---- masks, edge
     ++f.launches;
-    dec_masks_kernel<<<dim3((16 * T + 255) / 256, batch), 256, 0, stream>>>(F32(ws.up), F32(ws.ee), F32(ws.ef), F32(ws.hyper), masks, edge, g);
+    dec_masks_kernel<<<dim3(16 * T / 32, batch), 256, 0, stream>>>(F32(ws.up), F32(ws.ee), F32(ws.ef), F32(ws.hyper), masks, edge, g);
     CVLM_CUDA(cudaGetLastError());
     dec->last_launches = f.launches;
     return CVLM_OK;
