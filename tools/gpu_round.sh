@@ -17,7 +17,18 @@ timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench_$TAG.json 2> $O/benc
 echo "bench exit $?" | tee -a $O/round_$TAG.log
 tail -c 3000 $O/bench_$TAG.json | tee -a $O/round_$TAG.log
 tail -5 $O/bench_$TAG.err | tee -a $O/round_$TAG.log
+echo "=== mask decoder (8 f1)" | tee -a $O/round_$TAG.log
+timeout 600 python tools/decoder_bench.py --batch 32 --cascade --cpu > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
+echo "decoder bench exit $?" | tee -a $O/round_$TAG.log
+cut -c1-260 $O/decoder_bench_$TAG.json | tee -a $O/round_$TAG.log
 if [ "$2" == "noncu" ]; then exit 0; fi
+DEC="python tools/decoder_bench.py --batch 32 --steps 1 --warmup 1"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ncu_decoder_launches_$TAG.csv \
+    $DEC > $O/ncu_decoder_$TAG.log 2>&1
+echo "ncu decoder list exit $?" | tee -a $O/round_$TAG.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:dec_token_layer_kernel -s 2 -c 1 \
+    -o $O/prof_dec_token_$TAG -f $DEC > $O/ncu_full_dt_$TAG.log 2>&1
+echo "ncu full decoder token exit $?" | tee -a $O/round_$TAG.log
 KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|attn_global_tc2_kernel|attn_window_tc2_kernel|layernorm_kernel|ln_finalize_kernel|im2col|cast_bf16_kernel|cast_pad_rows_kernel|adapter_embed_kernel|layernorm_nchw_kernel'
 BENCH="python bench.py --steps 1 --warmup 3 --batch 32 --skip-cpu-baseline --skip-e2e --skip-decoder"
 echo "=== ncu launch list" | tee -a $O/round_$TAG.log
