@@ -924,7 +924,7 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     const DecWorkspace ws = plan(c, batch);
     if (workspace_bytes < ws.total)
         return set_error(CVLM_ERR_WORKSPACE, "decoder_forward: workspace %lld < %lld bytes", workspace_bytes, ws.total);
-    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(CVLM_ERR_ARG, "decoder_forward: workspace must be 1 KiB aligned");
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(CVLM_ERR_ARG, "decoder_forward: workspace must be 256-byte aligned");
     const int g = c.grid, T = g * g, nc = c.cond_tokens;
     const long long M = static_cast<long long>(T) * batch, P1 = 4 * M;
     if (static_cast<long long>(batch) * (4 * g + 2) * (4 * g + 2) >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: batch %d too large for one call (chunk it)", batch);
@@ -953,6 +953,28 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     if (const char* e = getenv("CVLM_DEC_CLUSTER")) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) csize = v;
+    }
+    // a cluster of `csize` CTAs with this much shared memory each must be schedulable: ask once per size, fall back
+    static int cluster_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // 0 unknown, 1 yes, -1 no
+    for (; csize > 1; csize >>= 1) {
+        if (cluster_ok[csize] == 0) {
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = csize;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(csize);
+            qc.blockDim = dim3(TOK_THREADS);
+            qc.dynamicSmemBytes = tok_smem;
+            qc.attrs = qa;
+            qc.numAttrs = 1;
+            int n = 0;
+            const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, dec_token_layer_kernel, &qc);
+            if (qe != cudaSuccess) cudaGetLastError();
+            cluster_ok[csize] = (qe == cudaSuccess && n > 0) ? 1 : -1;
+        }
+        if (cluster_ok[csize] == 1) break;
     }
     cudaLaunchAttribute tok_attr[1];
     tok_attr[0].id = cudaLaunchAttributeClusterDimension;

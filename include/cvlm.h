@@ -213,7 +213,7 @@ long long cvlm_decoder_last_launches(const cvlm_decoder* dec);
  *   masks  fp32 [batch, 4, 4g, 4g]  (all mask tokens; the caller slices like mask_decoder_edge.py:133-139)
  *   edge   fp32 [batch, 1, 4g, 4g]      iou_pred fp32 [batch, 4]
  *   hs     NULL or fp32 [batch, 6, 256]: the transformer's output tokens
- *   workspace: device, 1 KiB aligned, >= cvlm_decoder_workspace_bytes(dec, batch) */
+ *   workspace: device, 256-byte aligned, >= cvlm_decoder_workspace_bytes(dec, batch) */
 int cvlm_decoder_forward(cvlm_decoder* dec, const float* image_embeddings, const float* image_pe, const float* sparse_prompt,
                          const float* dense_prompt, int dense_batch, int batch, float* masks, float* edge, float* iou_pred,
                          float* hs, void* workspace, long long workspace_bytes, cvlm_stream_t stream);

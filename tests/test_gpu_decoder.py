@@ -169,3 +169,20 @@ def test_decoder_token_cluster_sizes(csize, monkeypatch):
         assert float((iou[b:b + 1].cpu() - want["iou"][:, 0:1]).abs().max()) < 1e-3
     again = run(dec, sd, emb, sparse)
     assert torch.equal(again[0], masks) and torch.equal(dec.last_hs, hs)      # deterministic run to run
+
+
+@pytest.mark.parametrize("g,nc,batch", [(8, 1, 1), (8, 8, 3), (32, 5, 2)])
+def test_decoder_edge_geometries(g, nc, batch):
+    # smallest embedding (64 keys: fewer keys per cluster rank than warps), one and the maximum number of prompt tokens
+    dec, sd = build(4)
+    gen = torch.Generator().manual_seed(100 + g + nc)
+    emb = torch.randn(batch, 256, g, g, generator=gen)
+    sparse = torch.randn(batch, nc, 256, generator=gen)
+    masks, edge, iou = run(dec, sd, emb, sparse, multimask=True)
+    assert masks.shape == (batch, 3, 4 * g, 4 * g) and edge.shape == (batch, 1, 4 * g, 4 * g) and iou.shape == (batch, 3)
+    for b in range(batch):
+        want = mdo.decode_all(sd, emb[b:b + 1], sparse[b:b + 1])
+        assert rel_l2(masks[b:b + 1].cpu(), want["masks"][:, 1:]) < TOL
+        assert rel_l2(edge[b:b + 1].cpu(), want["edge"]) < TOL
+        assert rel_l2(dec.last_hs[b:b + 1].cpu(), want["hs"]) < 3e-3
+        assert float((iou[b:b + 1].cpu() - want["iou"][:, 1:]).abs().max()) < 1e-3
