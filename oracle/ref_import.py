@@ -78,3 +78,22 @@ def build_reference_encoder(cfg):
         window_size=cfg.window_size,
         global_attn_indexes=tuple(cfg.global_attn_indexes),
     )
+
+
+def load_reference_alpha_clip_model():
+    """alpha_clip_rw/model.py of the reference (VisionTransformer_MaPLe: SURVEY.md 8 f2).  The file imports `loralib`
+    (absent from this image) at module scope but only touches it when lora_adapt=True, which the cascade never sets
+    (alpha_clip_rw/model.py:203-206, 263-267); an empty stand-in module lets the unmodified source load."""
+    path = os.path.join(REF_ROOT, "alpha_clip_rw", "model.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"reference Alpha-CLIP model not found at {path}")
+    name = "refalphaclip_model"
+    if name in sys.modules:
+        return sys.modules[name]
+    if "loralib" not in sys.modules:
+        sys.modules["loralib"] = types.ModuleType("loralib")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
