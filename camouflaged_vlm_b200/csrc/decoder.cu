@@ -935,19 +935,19 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     const int hid_floats = NTOK * c.mlp_dim > HID_MIN_FLOATS ? NTOK * c.mlp_dim : HID_MIN_FLOATS;
     const size_t tok_smem = static_cast<size_t>(SM_HID + hid_floats) * sizeof(float);
     if (tok_smem > 220 * 1024) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: mlp_dim %d needs too much shared memory", c.mlp_dim);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // per-device one-time setup (function attributes belong to the device's context); one process may drive several GPUs
+    int dev = 0, sms = 148;
+    CVLM_CUDA(cudaGetDevice(&dev));
+    CVLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static bool attr_done[64] = {};
+    static int cluster_ok[64][9] = {};      // per cluster size: 0 unknown, 1 schedulable, -1 not
+    const int di = dev & 63;
+    if (!attr_done[di]) {
         CVLM_CUDA(cudaFuncSetAttribute(dec_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CVLM_CUDA(cudaFuncSetAttribute(dec_token_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        attr_done[di] = true;
     }
     // CTAs per image on the token side: as many as keep the whole batch in one wave (CVLM_DEC_CLUSTER overrides: tests)
-    int sms = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     int csize = 8;
     while (csize > 1 && batch * csize > sms) csize >>= 1;
     if (const char* e = getenv("CVLM_DEC_CLUSTER")) {
@@ -955,9 +955,8 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
         if (v == 1 || v == 2 || v == 4 || v == 8) csize = v;
     }
     // a cluster of `csize` CTAs with this much shared memory each must be schedulable: ask once per size, fall back
-    static int cluster_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // 0 unknown, 1 yes, -1 no
     for (; csize > 1; csize >>= 1) {
-        if (cluster_ok[csize] == 0) {
+        if (cluster_ok[di][csize] == 0) {
             cudaLaunchAttribute qa[1];
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = csize;
@@ -972,9 +971,9 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
             int n = 0;
             const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, dec_token_layer_kernel, &qc);
             if (qe != cudaSuccess) cudaGetLastError();
-            cluster_ok[csize] = (qe == cudaSuccess && n > 0) ? 1 : -1;
+            cluster_ok[di][csize] = (qe == cudaSuccess && n > 0) ? 1 : -1;
         }
-        if (cluster_ok[csize] == 1) break;
+        if (cluster_ok[di][csize] == 1) break;
     }
     cudaLaunchAttribute tok_attr[1];
     tok_attr[0].id = cudaLaunchAttributeClusterDimension;
