@@ -121,17 +121,19 @@ __device__ __forceinline__ void g2_scale_cols(uint32_t addr, float f) {
     tmem_st_wait();
 }
 
-template <int HD, int POLY>
+// PLAIN = true: the same pipeline as a plain softmax(q k^T / sqrt(hd)) v over `L` tokens per image (any L >= 1, no
+// relative-position terms): key units beyond L are masked in the last unit, query rows beyond L are not stored.
+template <int HD, int POLY, bool PLAIN>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmRelH, const __grid_constant__ CUtensorMap tmRelW,
-                       __nv_bfloat16* __restrict__ out, int heads, int D, float scale_log2) {
+                       __nv_bfloat16* __restrict__ out, int heads, int D, float scale_log2, int L) {
     constexpr bool HI = HD > 64;
     constexpr uint32_t Q_BYTES = (HI ? 2 : 1) * G2_QTILE;
     constexpr uint32_t KV_BYTES = (HI ? 2 : 1) * G2_KTILE;
-    constexpr int NK = 4096 / G2_UNIT;              // 64 key units
-    constexpr int NREL = 4;                         // rel_pos_w rows 0..63 / 64..127, rel_pos_h slice rows 0..63 / 64..127
-    constexpr int NU = NK + NREL;
+    const int NK = PLAIN ? (L + G2_UNIT - 1) / G2_UNIT : 4096 / G2_UNIT;   // key units (64 for the 64x64 grid)
+    constexpr int NREL = PLAIN ? 0 : 4;             // rel_pos_w rows 0..63 / 64..127, rel_pos_h slice rows 0..63 / 64..127
+    const int NU = NK + NREL;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     auto sQ = [&](int t) { return base + G2_OFF_Q + t * G2_QSTAGE; };
@@ -153,7 +155,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int y0 = 4 * qb;                          // first grid row of this CTA's queries
-    const int tok0 = b * 4096;
+    const int tok0 = b * (PLAIN ? L : 4096);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -202,10 +204,10 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             auto produce_k = [&](int u) {
                 mbar_wait(k_empty(kst), kph ^ 1u);
                 mbar_arrive_expect_tx(k_full(kst), KV_BYTES);
-                if (u < 2) {
+                if (!PLAIN && u < 2) {
                     tma_load_2d(sK(kst), &tmRelW, k_full(kst), 0, u * 64);
                     if (HI) tma_load_2d(sK(kst) + G2_KTILE, &tmRelW, k_full(kst), 64, u * 64);
-                } else if (u < 4) {
+                } else if (!PLAIN && u < 4) {
                     tma_load_2d(sK(kst), &tmRelH, k_full(kst), 0, y0 + (u - 2) * 64);
                     if (HI) tma_load_2d(sK(kst) + G2_KTILE, &tmRelH, k_full(kst), 64, y0 + (u - 2) * 64);
                 } else {
@@ -289,7 +291,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int qrow = r >> 6, qx = r & 63;
         const uint32_t t_s = tmem_base + lane_addr + t * 128;
         const uint32_t t_o = tmem_base + lane_addr + G2_COL_O + t * G2_O_STRIDE;
-        float trow[256];                            // this row of T_w (0..127) and T_h (128..255): dynamic indexing -> local memory
+        float trow[PLAIN ? 1 : 256];                // this row of T_w (0..127) and T_h (128..255): dynamic indexing -> local memory
         uint32_t va[32], vb[32];
 #pragma unroll 1
         for (int u = 0; u < NREL; ++u) {
@@ -310,7 +312,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // rel_w[q, kx] = T_w[q][qx - kx + 63] (image_encoder.py:576-586): the same for every key unit
         uint64_t tw2[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tw2[i] = f32x2_pack(trow[qx + 63 - 2 * i], trow[qx + 62 - 2 * i]);
+        for (int i = 0; i < 32; ++i) tw2[i] = PLAIN ? 0ull : f32x2_pack(trow[PLAIN ? 0 : qx + 63 - 2 * i], trow[PLAIN ? 0 : qx + 62 - 2 * i]);
         const uint64_t scale2 = f32x2_pack(scale_log2, scale_log2);
         float m_used = 0.f, l = 0.f;
 
@@ -318,7 +320,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int j = 0; j < NK; ++j) {
             const int u = j + NREL, bb = u & 1;
             // key row ky = j;  rel_h[q, ky] = T_h[q][qy - ky + 63 - y0],  qy = y0 + 2t + qrow
-            const float th = trow[128 + 2 * t + qrow + 63 - j];
+            const float th = PLAIN ? 0.f : trow[PLAIN ? 0 : 128 + 2 * t + qrow + 63 - j];
             mbar_wait(s_full(t, bb), static_cast<uint32_t>((u >> 1) & 1));
             tc_fence_after();
             const uint32_t t_su = t_s + bb * 64;
@@ -326,6 +328,15 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tmem_ld_32x32(t_su + 32, vb);
             tmem_ld_wait(va);
             tmem_ld_wait(vb);
+            if (PLAIN && j == NK - 1 && L - j * G2_UNIT < G2_UNIT) {
+                // keys beyond the sequence: logit -inf, so their exponential is (as good as) zero
+                const int nvalid = L - j * G2_UNIT;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i >= nvalid) va[i] = 0xff800000u;
+                    if (32 + i >= nvalid) vb[i] = 0xff800000u;
+                }
+            }
             if (j == 0) {
                 float t0, t1;
                 f32x2_unpack(tw2[0], t0, t1);
@@ -385,10 +396,12 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_after();
         const float inv = 1.0f / l;
         __nv_bfloat16* orow = out + (static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * D + head * HD;
+        const bool live = !PLAIN || qb * 256 + t * 128 + r < L;        // query rows beyond the sequence are not stored
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             tmem_ld_32x32(t_o + c * 32, va);
             tmem_ld_wait(va);
+            if (!live) continue;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
                 uint4 o4;
@@ -404,7 +417,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tmem_ld_32x16(t_o + 64, w16);
             tmem_ld_wait16(w16);
 #pragma unroll
-            for (int i = 0; i < 16; i += 8) {
+            for (int i = 0; i < (live ? 16 : 0); i += 8) {
                 uint4 o4;
                 o4.x = pack_bf16(__uint_as_float(w16[i]) * inv, __uint_as_float(w16[i + 1]) * inv);
                 o4.y = pack_bf16(__uint_as_float(w16[i + 2]) * inv, __uint_as_float(w16[i + 3]) * inv);
@@ -422,15 +435,15 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
 }
 
-template <int HD, int POLY>
+template <int HD, int POLY, bool PLAIN>
 static int launch_global_tc2(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                             cudaStream_t stream) {
+                             int tokens, cudaStream_t stream) {
     const int D = heads * HD;
     CUtensorMap tq, tkv, th, tw;
     MapSpec s = map_spec_zero();
     s.ptr = qkv;
     s.rank = 3;
-    s.dims[0] = HD; s.dims[1] = 3ull * heads; s.dims[2] = 4096ull * batch;
+    s.dims[0] = HD; s.dims[1] = 3ull * heads; s.dims[2] = static_cast<unsigned long long>(tokens) * batch;
     s.strides[0] = HD * 2ull; s.strides[1] = 3ull * D * 2;
     s.box[0] = 64; s.box[1] = 1; s.box[2] = 128;
     CVLM_TRY(make_tensor_map_bf16(&tq, s));
@@ -441,11 +454,16 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
     r.dims[0] = HD; r.dims[1] = 127;
     r.strides[0] = HD * 2ull;
     r.box[0] = 64; r.box[1] = G2_UNIT;
-    r.ptr = relh;
-    CVLM_TRY(make_tensor_map_bf16(&th, r));
-    r.ptr = relw;
-    CVLM_TRY(make_tensor_map_bf16(&tw, r));
-    auto kern = attn_global_tc2_kernel<HD, POLY>;
+    if (PLAIN) {
+        th = tkv;       // never read
+        tw = tkv;
+    } else {
+        r.ptr = relh;
+        CVLM_TRY(make_tensor_map_bf16(&th, r));
+        r.ptr = relw;
+        CVLM_TRY(make_tensor_map_bf16(&tw, r));
+    }
+    auto kern = attn_global_tc2_kernel<HD, POLY, PLAIN>;
     CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     {   // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
         cudaFuncAttributes fa;
@@ -453,9 +471,9 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
         if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
             return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
     }
-    dim3 grid(16, heads, batch);
+    dim3 grid((tokens + 255) / 256, heads, batch);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eG2;
-    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2);
+    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
@@ -464,11 +482,11 @@ template <int HD>
 static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const void* relh, const void* relw, int batch,
                                   int heads, cudaStream_t stream) {
     switch (poly) {
-        case 0: return launch_global_tc2<HD, 0>(qkv, out, relh, relw, batch, heads, stream);
-        case 2: return launch_global_tc2<HD, 2>(qkv, out, relh, relw, batch, heads, stream);
-        case 4: return launch_global_tc2<HD, 4>(qkv, out, relh, relw, batch, heads, stream);
-        case 6: return launch_global_tc2<HD, 6>(qkv, out, relh, relw, batch, heads, stream);
-        case 8: return launch_global_tc2<HD, 8>(qkv, out, relh, relw, batch, heads, stream);
+        case 0: return launch_global_tc2<HD, 0, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
+        case 2: return launch_global_tc2<HD, 2, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
+        case 4: return launch_global_tc2<HD, 4, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
+        case 6: return launch_global_tc2<HD, 6, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
+        case 8: return launch_global_tc2<HD, 8, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
         default: return set_error(CVLM_ERR_ARG, "CVLM_ATTN_POLY must be 0, 2, 4, 6 or 8");
     }
 }
@@ -482,6 +500,19 @@ int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, co
     if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream);
     if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: head_dim %d", head_dim);
+}
+
+// Plain attention softmax(q k^T / sqrt(hd)) v over `tokens` tokens per image (no relative-position terms): the visual
+// tower of Alpha-CLIP (alpha_clip_rw/model.py:224-256 with the default arguments) on the same tcgen05
+// pipeline.  qkv bf16 [batch * tokens, 3, heads, hd] (the output of in_proj), out bf16 [batch * tokens, heads * hd].
+int attention_plain_tc2_launch(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
+                               cudaStream_t stream) {
+    if (batch > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch exceeds grid.z; split the batch");
+    if (tokens < 1 || heads < 1) return set_error(CVLM_ERR_ARG, "attention_plain: tokens %d heads %d", tokens, heads);
+    if (static_cast<long long>(tokens) * batch >= (1ll << 31)) return set_error(CVLM_ERR_UNSUPPORTED, "attention_plain: too many tokens");
+    if (head_dim == 80) return launch_global_tc2<80, 4, true>(qkv, out, nullptr, nullptr, batch, heads, tokens, stream);
+    if (head_dim == 64) return launch_global_tc2<64, 4, true>(qkv, out, nullptr, nullptr, batch, heads, tokens, stream);
+    return set_error(CVLM_ERR_UNSUPPORTED, "attention_plain: head_dim %d (64 or 80)", head_dim);
 }
 
 }  // namespace cvlm

@@ -77,6 +77,9 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
                                 int head_dim, cudaStream_t stream);
 
+int attention_plain_tc2_launch(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
+                               cudaStream_t stream);
+
 int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                                 int heads, int head_dim, cudaStream_t stream);
 

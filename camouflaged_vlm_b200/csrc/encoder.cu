@@ -543,6 +543,12 @@ int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const v
                             static_cast<cudaStream_t>(stream));
 }
 
+int cvlm_op_attention_plain(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
+                            cvlm_stream_t stream) {
+    if (!qkv || !out) return set_error(CVLM_ERR_ARG, "attention_plain: null pointer");
+    return attention_plain_tc2_launch(qkv, out, batch, tokens, heads, head_dim, static_cast<cudaStream_t>(stream));
+}
+
 int cvlm_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,
                       int cols, float eps, cvlm_stream_t stream) {
     return layernorm_launch(x, gamma, beta, out, out_bf16, rows, cols, eps, static_cast<cudaStream_t>(stream));

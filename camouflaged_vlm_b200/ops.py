@@ -83,6 +83,16 @@ def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tenso
     return out
 
 
+def attention_plain(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(head_dim)) v per image, no relative-position terms; qkv bf16 [batch * tokens, 3 * heads * hd]."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (batch * tokens, 3 * heads * head_dim)
+    out = torch.empty(qkv.shape[0], heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_attention_plain(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, head_dim,
+                                                   _lib.stream_ptr()), "cvlm_op_attention_plain")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype=torch.bfloat16):
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.is_contiguous()

@@ -144,6 +144,14 @@ int cvlm_op_ln_finalize(const float* partial, int groups, int width, float eps, 
 int cvlm_op_attention(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
                       int grid_side, int window, int heads, int head_dim, cvlm_stream_t stream);
 
+/* Plain attention softmax(q k^T / sqrt(head_dim)) v over `tokens` tokens per image, no relative-position terms
+ * (Attention.forward of the Alpha-CLIP visual tower, alpha_clip_rw/model.py:224-256 with default arguments; the kernel
+ * of SURVEY.md 8 f2, exposed ahead of that row).  Same tcgen05 pipeline as the global attention.
+ * qkv bf16 [batch * tokens, 3 * heads * head_dim] laid out (q | k | v) x heads x head_dim, out bf16
+ * [batch * tokens, heads * head_dim]; head_dim 64 or 80; any tokens >= 1. */
+int cvlm_op_attention_plain(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
+                            cvlm_stream_t stream);
+
 /* nn.LayerNorm over the last dim of fp32 [rows, cols]; out bf16 (out_bf16=1) or fp32. */
 int cvlm_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_bf16,
                       long long rows, int cols, float eps, cvlm_stream_t stream);

@@ -256,3 +256,23 @@ def test_gemm_random_shapes(gemm_mode):
         assert _rel(got, want) < 2e-5, (it, m, n, k, gelu)
         got16 = ops.gemm_bf16(a, b, bias=bias, residual=res, gelu=gelu, out_dtype=torch.bfloat16)
         assert _rel(got16.float(), want) < 4e-3, (it, m, n, k, gelu)
+
+
+@pytest.mark.parametrize("batch,tokens,heads,hd", [(2, 579, 16, 64), (1, 64, 2, 64), (3, 65, 2, 80), (2, 256, 1, 64),
+                                                   (1, 257, 3, 80), (2, 1, 2, 64), (1, 1000, 2, 64)])
+def test_attention_plain(batch, tokens, heads, hd):
+    """The global-attention pipeline without relative-position terms over an arbitrary sequence length (ragged last key
+    unit masked, query rows beyond the sequence not stored) against fp32 softmax attention on the same bf16 inputs.
+    579 tokens x 16 heads x 64 is the Alpha-CLIP ViT-L/14@336 tower with two MaPLe context tokens."""
+    d = heads * hd
+    qkv = _randn(batch * tokens, 3 * d, seed=90 + tokens, dtype=torch.bfloat16, scale=0.8)
+    q, k, v = (t.reshape(batch, tokens, heads, hd).permute(0, 2, 1, 3) for t in qkv.float().split(d, dim=1))
+    want = (torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(batch * tokens, d)
+    got = ops.attention_plain(qkv, batch, tokens, heads, hd).float()
+    assert torch.isfinite(got).all()
+    assert _rel(got, want) < 8e-3
+    # the last query block is ragged: nothing may be written past the last token
+    from camouflaged_vlm_b200 import _lib
+    out = torch.full((batch * tokens + 256, d), 7.0, device=DEV, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_attention_plain(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, hd, _lib.stream_ptr()))
+    assert torch.equal(out[:batch * tokens].float(), got) and bool((out[batch * tokens:] == 7.0).all())
