@@ -42,6 +42,12 @@ class DecoderConfigC(C.Structure):
                 ("ln_eps", C.c_float), ("ln2d_eps", C.c_float)]
 
 
+class VitConfigC(C.Structure):
+    """struct cvlm_vit_config (include/cvlm.h)."""
+    _fields_ = [("input_resolution", C.c_int), ("patch_size", C.c_int), ("width", C.c_int), ("layers", C.c_int),
+                ("heads", C.c_int), ("output_dim", C.c_int), ("n_ctx", C.c_int), ("ln_eps", C.c_float)]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into libcvlm_b200.so (no GPU needed)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
@@ -108,6 +114,13 @@ _SIGS = {
     "cvlm_decoder_last_launches": (C.c_longlong, [C.c_void_p]),
     "cvlm_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_vit_create": (C.c_int, [C.POINTER(VitConfigC), C.POINTER(C.c_void_p)]),
+    "cvlm_vit_destroy": (C.c_int, [C.c_void_p]),
+    "cvlm_vit_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
+    "cvlm_vit_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "cvlm_vit_last_launches": (C.c_longlong, [C.c_void_p]),
+    "cvlm_vit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_op_bilinear_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p]),
 }

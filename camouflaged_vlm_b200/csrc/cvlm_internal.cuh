@@ -43,7 +43,7 @@ struct GemmArgs {
     void* out = nullptr;       // fp32 or bf16 [M, ldo]
     long long ldo = 0;
     int out_bf16 = 0;
-    int act_gelu = 0;
+    int act_gelu = 0;          // 1: exact-erf GELU (nn.GELU), 2: QuickGELU x * sigmoid(1.702 x) (CLIP)
     // LayerNorm folded around the GEMMs.  nn.LayerNorm (image_encoder.py:430-446 norm1 / norm2) sits between a GEMM
     // that writes the fp32 residual stream and a GEMM that reads its normalised bf16 copy.  Instead of a separate
     // pass over x, the PRODUCER (fp32 path) also stores bf16(x) and, per row and column group, (sum x, sum x^2);

@@ -118,6 +118,11 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
 //   F_STATIC    the epilogue type is a compile-time fact: F_BF16 (bf16 output), F_GELU, F_RES (fp32 residual) say which;
 //               without it those three are read from GemmEpi at run time (stem / adapter / neck GEMMs)
 constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64;
+// QuickGELU of CLIP (alpha_clip_rw/model.py:171-173): x * sigmoid(1.702 x); GemmArgs::act_gelu == 2
+__device__ __forceinline__ float quick_gelu(float x) {
+    return x * __frcp_rn(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x));
+}
+
 template <bool PAIR, int FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -369,7 +374,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         if (row < M && col_ok) {
                             x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
                             if (act_gelu) {
-                                x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                                if ((FEAT & F_RARE) && ep.act_gelu == 2) {
+                                    x.x = quick_gelu(x.x); x.y = quick_gelu(x.y); x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
+                                } else {
+                                    x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                                }
                             }
                             if (use_res) {
                                 x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
@@ -419,8 +428,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
                             }
                             if (act_gelu) {
+                                if ((FEAT & F_RARE) && ep.act_gelu == 2) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
+                                    for (int e = 0; e < 4; ++e) {
+                                        float lo, hi;
+                                        f32x2_unpack(y[e], lo, hi);
+                                        y[e] = f32x2_pack(quick_gelu(lo), quick_gelu(hi));
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
+                                }
                             }
                             if (has_res) {
                                 const long long rrow = ((FEAT & F_RARE) && ep.res_row_mod > 0) ? row % ep.res_row_mod : brow + row;
@@ -673,7 +691,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     ep.tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = nbatch * tiles_m * tiles_n;
     // the exact shape of this call's epilogue; launch_variant maps the four block GEMMs to their own kernels
-    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0;
+    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0 || a.act_gelu == 2;
     const bool producer = a.copy_bf16 != nullptr && a.stat_out != nullptr;
     int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.residual ? F_RES : 0) |
                (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0);

@@ -226,6 +226,38 @@ int cvlm_decoder_forward(cvlm_decoder* dec, const float* image_embeddings, const
                          const float* dense_prompt, int dense_batch, int batch, float* masks, float* edge, float* iou_pred,
                          float* hs, void* workspace, long long workspace_bytes, cvlm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Alpha-CLIP visual tower with MaPLe deep prompts: VisionTransformer_MaPLe.forward
+ * (alpha_clip_rw/model.py:507-563), called as image_encoder(images, masks, shared_ctx, deep_prompts)
+ * (cocotrainers/mapleAlphaCLIP.py:272, 286).  csrc/alpha_clip.cu.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cvlm_vit_config {
+    int input_resolution; /* 336 */
+    int patch_size;       /* 14 (even, divides the resolution) */
+    int width;            /* 1024 (multiple of 128, <= 2048) */
+    int layers;           /* 24 */
+    int heads;            /* 16 (width / heads must be 64 or 80) */
+    int output_dim;       /* 768 (multiple of 8) */
+    int n_ctx;            /* MaPLe context tokens appended to the sequence (design_details['maple_length']) */
+    float ln_eps;         /* 1e-5 */
+} cvlm_vit_config;
+
+typedef struct cvlm_vit cvlm_vit;
+
+int cvlm_vit_create(const cvlm_vit_config* cfg, cvlm_vit** out);
+int cvlm_vit_destroy(cvlm_vit* vit);
+/* fp32 parameters under the reference's state_dict names, plus the bf16 copies listed in
+ * camouflaged_vlm_b200/alpha_clip.py (pack_vit_weights). */
+int cvlm_vit_set_tensor(cvlm_vit* vit, const char* name, const void* dev_ptr, long long nbytes);
+long long cvlm_vit_workspace_bytes(const cvlm_vit* vit, int batch);
+long long cvlm_vit_last_launches(const cvlm_vit* vit);
+
+/*   images fp32 NCHW [batch, 3, R, R]      alpha fp32 [batch, 1, R, R]
+ *   shared_ctx fp32 [n_ctx, width]         deep_prompts fp32 [n_deep, n_ctx, width] (NULL when n_deep == 0)
+ *   out fp32 [batch, output_dim]           workspace: device, 256-byte aligned, >= cvlm_vit_workspace_bytes(vit, batch) */
+int cvlm_vit_forward(cvlm_vit* vit, const float* images, const float* alpha, const float* shared_ctx, const float* deep_prompts,
+                     int n_deep, int batch, float* out, void* workspace, long long workspace_bytes, cvlm_stream_t stream);
+
 /* F.interpolate(mode="bilinear", align_corners=False) on `planes` fp32 images [in_h, in_w] -> [out_h, out_w]
  * (postprocess_masks, models/sam_maskdecoder_edge.py:359-388). */
 int cvlm_op_bilinear_resize(const float* in, float* out, long long planes, int in_h, int in_w, int out_h, int out_w,

@@ -41,6 +41,7 @@ class VitConfig:
 
 
 SMALL = VitConfig(input_resolution=56, patch_size=14, width=64, layers=3, heads=4, output_dim=32, n_ctx=2)
+SMALL_HD64 = VitConfig(input_resolution=70, patch_size=14, width=128, layers=4, heads=2, output_dim=32, n_ctx=2)   # CUDA-path fixture
 
 
 def vit_param_shapes(cfg: VitConfig) -> Dict[str, Tuple[int, ...]]:

@@ -31,17 +31,17 @@ def seeded_inputs(cfg, batch, seed=0):
 
 
 def main():
-    cfg = aco.SMALL
-    sd = aco.seeded_vit_state(cfg, 0)
-    vit = reference_tower(cfg, sd)
-    image, alpha = seeded_inputs(cfg, 2)
-    shared, deep = aco.seeded_prompts(cfg, depth=3)
-    with torch.no_grad():
-        out = vit(image, alpha, shared, deep)
-        out_shallow = vit(image, alpha, shared, [])
-    np.savez_compressed(os.path.join(GOLDEN, "alpha_clip_small.npz"), image=image.numpy(), alpha=alpha.numpy(),
-                        out=out.numpy(), out_shallow=out_shallow.numpy())
-    print("[golden] alpha_clip_small", tuple(out.shape), float(out.std()))
+    for name, cfg, depth in (("small", aco.SMALL, 3), ("small_hd64", aco.SMALL_HD64, 3)):
+        sd = aco.seeded_vit_state(cfg, 0)
+        vit = reference_tower(cfg, sd)
+        image, alpha = seeded_inputs(cfg, 2)
+        shared, deep = aco.seeded_prompts(cfg, depth=depth)
+        with torch.no_grad():
+            out = vit(image, alpha, shared, deep)
+            out_shallow = vit(image, alpha, shared, [])
+        np.savez_compressed(os.path.join(GOLDEN, f"alpha_clip_{name}.npz"), image=image.numpy(), alpha=alpha.numpy(),
+                            out=out.numpy(), out_shallow=out_shallow.numpy())
+        print(f"[golden] alpha_clip_{name}", tuple(out.shape), float(out.std()))
 
 
 if __name__ == "__main__":
