@@ -117,10 +117,17 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
 //   F_RARE      batched mode, |.| output, row-periodic residual (stem / high-pass GEMMs)
 //   F_STATIC    the epilogue type is a compile-time fact: F_BF16 (bf16 output), F_GELU, F_RES (fp32 residual) say which;
 //               without it those three are read from GemmEpi at run time (stem / adapter / neck GEMMs)
-constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64;
+constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64, F_QUICK = 128;
 // QuickGELU of CLIP (alpha_clip_rw/model.py:171-173): x * sigmoid(1.702 x); GemmArgs::act_gelu == 2
 __device__ __forceinline__ float quick_gelu(float x) {
     return x * __frcp_rn(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x));
+}
+
+// the same on a pair: x / (1 + 2^(-1.702 log2(e) x)), packed multiplies / adds around the two MUFU pairs
+__device__ __forceinline__ uint64_t quick_gelu2(uint64_t x) {
+    const uint64_t c = f32x2_pack(1.702f * 1.4426950408889634f, 1.702f * 1.4426950408889634f);
+    const uint64_t one = f32x2_pack(1.0f, 1.0f);
+    return f32x2_mul(x, f32x2_rcp(f32x2_add(one, f32x2_ex2_neg(f32x2_mul(x, c)))));
 }
 
 template <bool PAIR, int FEAT>
@@ -274,6 +281,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         // 8 lanes x 16 B = one full 128-byte line of the fp32 output / residual per row.
         const bool out_bf16 = (FEAT & F_STATIC) ? (FEAT & F_BF16) != 0 : ep.out_bf16 != 0;
         const bool act_gelu = (FEAT & F_STATIC) ? (FEAT & F_GELU) != 0 : ep.act_gelu != 0;
+        const bool act_quick = (FEAT & F_STATIC) ? (FEAT & F_QUICK) != 0 : ep.act_gelu == 2;      // QuickGELU instead of erf
         const bool has_res = (FEAT & F_STATIC) ? (FEAT & F_RES) != 0 : ep.residual != nullptr;
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may touch (warp_id % 4)
@@ -374,7 +382,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                         if (row < M && col_ok) {
                             x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
                             if (act_gelu) {
-                                if ((FEAT & F_RARE) && ep.act_gelu == 2) {
+                                if (act_quick) {
                                     x.x = quick_gelu(x.x); x.y = quick_gelu(x.y); x.z = quick_gelu(x.z); x.w = quick_gelu(x.w);
                                 } else {
                                     x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
@@ -428,13 +436,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
                             }
                             if (act_gelu) {
-                                if ((FEAT & F_RARE) && ep.act_gelu == 2) {
+                                if (act_quick) {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        float lo, hi;
-                                        f32x2_unpack(y[e], lo, hi);
-                                        y[e] = f32x2_pack(quick_gelu(lo), quick_gelu(hi));
-                                    }
+                                    for (int e = 0; e < 4; ++e) y[e] = quick_gelu2(y[e]);
                                 } else {
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
@@ -608,6 +612,8 @@ constexpr int V_QKV = F_STATIC | F_BF16 | F_CONSUMER;           // norm1 + qkv
 constexpr int V_PROJ = F_STATIC | F_RES;                        // proj + shortcut
 constexpr int V_LIN1 = F_STATIC | F_BF16 | F_GELU;              // lin1 + GELU
 constexpr int V_LIN2 = F_STATIC | F_RES | F_PRODUCER;           // lin2 + shortcut, feeds the next norm1
+constexpr int V_PLAIN = F_STATIC | F_BF16;                      // bias only, bf16 out (in_proj of the CLIP tower)
+constexpr int V_LIN1Q = F_STATIC | F_BF16 | F_GELU | F_QUICK;   // c_fc + QuickGELU of the CLIP tower
 constexpr int V_ANY = F_PRODUCER | F_CONSUMER | F_RARE;         // run-time epilogue type, every feature
 template <typename... Args>
 static int launch_variant(bool pair, int feat, Args&&... args) {
@@ -617,6 +623,8 @@ static int launch_variant(bool pair, int feat, Args&&... args) {
             case V_PROJ: return launch_kernel<true, V_PROJ>(args...);
             case V_LIN1: return launch_kernel<true, V_LIN1>(args...);
             case V_LIN2: return launch_kernel<true, V_LIN2>(args...);
+            case V_PLAIN: return launch_kernel<true, V_PLAIN>(args...);
+            case V_LIN1Q: return launch_kernel<true, V_LIN1Q>(args...);
             default: return launch_kernel<true, V_ANY>(args...);
         }
     }
@@ -625,6 +633,8 @@ static int launch_variant(bool pair, int feat, Args&&... args) {
         case V_PROJ: return launch_kernel<false, V_PROJ>(args...);
         case V_LIN1: return launch_kernel<false, V_LIN1>(args...);
         case V_LIN2: return launch_kernel<false, V_LIN2>(args...);
+        case V_PLAIN: return launch_kernel<false, V_PLAIN>(args...);
+        case V_LIN1Q: return launch_kernel<false, V_LIN1Q>(args...);
         default: return launch_kernel<false, V_ANY>(args...);
     }
 }
@@ -691,9 +701,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     ep.tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = nbatch * tiles_m * tiles_n;
     // the exact shape of this call's epilogue; launch_variant maps the four block GEMMs to their own kernels
-    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0 || a.act_gelu == 2;
+    const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0;
     const bool producer = a.copy_bf16 != nullptr && a.stat_out != nullptr;
-    int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.residual ? F_RES : 0) |
+    int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.act_gelu == 2 ? F_QUICK : 0) | (a.residual ? F_RES : 0) |
                (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0);
     if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || !a.bias || n_run < BN) feat = V_ANY;
     return launch_variant(pair, feat, total_tiles, stream, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, nbatch * tiles_m, tiles_n, ep);
