@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-interm", action="store_true", help="call forward(x) instead of forward(x, interm=True)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--skip-decoder", action="store_true", help="skip the mask-decoder / cascade leg (SURVEY 8 f1)")
+    ap.add_argument("--skip-decoder", action="store_true", help="skip the mask-decoder / cascade / CLIP-tower legs (SURVEY 8 f1, f2)")
     return ap.parse_args()
 
 
@@ -375,6 +375,40 @@ def run_ours(args):
         del dec
         torch.cuda.empty_cache()
 
+    # ---- the Alpha-CLIP ViT-L/14@336 visual tower with MaPLe prompts (the cascade runs it twice per
+    # image); reported beside the headline like the decoder
+    f2 = None
+    if rank == 0 and world == 1 and not args.skip_decoder:
+        from camouflaged_vlm_b200 import alpha_clip as ac
+        tw = ac.VisionTransformer_MaPLe(336, 14, 1024, 24, 16, 768, design_details={"trainer": "MaPLe", "maple_length": 2}).eval()
+        gen = torch.Generator().manual_seed(2)
+        with torch.no_grad():
+            for n, p in tw.named_parameters():
+                std = 0.5 if n.startswith("conv1") else 1024 ** -0.5
+                p.copy_(torch.randn(p.shape, generator=gen) * std + (1.0 if (p.dim() == 1 and n.endswith("weight")) else 0.0))
+        tw = tw.to(dev)
+        timg = torch.randn(B, 3, 336, 336, generator=gen).to(dev)
+        talpha = (torch.rand(B, 1, 336, 336, generator=gen) > 0.5).float().to(dev)
+        tshared = (torch.randn(2, 1024, generator=gen) * 0.02).to(dev)
+        tdeep = [(torch.randn(2, 1024, generator=gen) * 0.02).to(dev) for _ in range(8)]
+        with torch.no_grad():
+            for _ in range(3):
+                tw(timg, talpha, tshared, tdeep)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                tw(timg, talpha, tshared, tdeep)
+            e1.record()
+            torch.cuda.synchronize()
+        tms = e0.elapsed_time(e1) / 10
+        tflop = B * (24 * (2.0 * 579 * 1024 * 12 * 1024 + 4.0 * 579 * 579 * 1024) + 2.0 * 576 * 1024 * 784) / (tms * 1e-3) / 1e12
+        f2 = {"metric": "alpha_clip_vit_l14_336_tower_img_per_s", "value": B / tms * 1e3, "unit": UNIT, "ms_per_step": tms,
+              "gpu_launches": int(tw.last_launch_count), "achieved_tflops": tflop, "frac_of_sustained": tflop / load_peaks()["sustained"],
+              "workload": f"VisionTransformer_MaPLe ViT-L/14@336 on {B} images, 579 tokens (2 context tokens, 8 deeper prompts), "
+                          "one pass (the cascade runs two per image), random-init weights"}
+        del tw
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -391,7 +425,7 @@ def run_ours(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels, "mask_decoder": f1,
+            "cpu_baseline": cpu, "kernels": kernels, "mask_decoder": f1, "alpha_clip_tower": f2,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

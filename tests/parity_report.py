@@ -95,6 +95,38 @@ def main(out_path):
     print("mask decoder:", json.dumps(d))
     del m, dec
     torch.cuda.empty_cache()
+    # the CUDA Alpha-CLIP / MaPLe tower (8 f2): reference golden (small) and the oracle at ViT-L/14@336
+    from camouflaged_vlm_b200 import alpha_clip as ac
+    from oracle import alpha_clip_oracle as aco
+
+    def tower(cfg, seed):
+        t = ac.VisionTransformer_MaPLe(cfg.input_resolution, cfg.patch_size, cfg.width, cfg.layers, cfg.heads, cfg.output_dim,
+                                       design_details={"trainer": "MaPLe", "maple_length": cfg.n_ctx}).eval()
+        tsd = aco.seeded_vit_state(cfg, seed)
+        t.load_state_dict(tsd, strict=True)
+        return t.cuda(), tsd
+
+    gt = np.load(os.path.join(GOLDEN, "alpha_clip_small_hd64.npz"))
+    t, tsd = tower(aco.SMALL_HD64, 0)
+    sh, dp = aco.seeded_prompts(aco.SMALL_HD64, depth=3)
+    with torch.no_grad():
+        o = t(torch.from_numpy(gt["image"]).cuda(), torch.from_numpy(gt["alpha"]).cuda(), sh.cuda(), [d.cuda() for d in dp])
+    tw = {"small_golden_rel_l2": orc.rel_l2(o.cpu(), torch.from_numpy(gt["out"]))}
+    cfgL = aco.VitConfig()
+    t, tsd = tower(cfgL, 1)
+    sh, dp = aco.seeded_prompts(cfgL, depth=9, seed=1)
+    gen = torch.Generator().manual_seed(3)
+    im = torch.randn(2, 3, 336, 336, generator=gen)
+    al = (torch.rand(2, 1, 336, 336, generator=gen) > 0.5).float()
+    with torch.no_grad():
+        o = t(im.cuda(), al.cuda(), sh.cuda(), [d.cuda() for d in dp])
+    w = aco.vit_maple_forward(tsd, cfgL, im, al, sh, dp)
+    tw["vit_l14_336_rel_l2"] = orc.rel_l2(o.cpu(), w)
+    tw["vit_l14_336_min_cosine"] = float(torch.nn.functional.cosine_similarity(o.cpu(), w, dim=-1).min())
+    rep["alpha_clip_tower"] = tw
+    print("alpha-clip tower:", json.dumps(tw))
+    del t
+    torch.cuda.empty_cache()
     # how much does the cuFFT high-pass depend on the batch it is computed in?
     cfg = PRESETS["vit_h"]
     x = seeded_images(cfg, 2).cuda()
