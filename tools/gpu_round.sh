@@ -21,7 +21,21 @@ echo "=== mask decoder (8 f1)" | tee -a $O/round_$TAG.log
 timeout 600 python tools/decoder_bench.py --batch 32 --cascade --cpu > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
 echo "decoder bench exit $?" | tee -a $O/round_$TAG.log
 cut -c1-260 $O/decoder_bench_$TAG.json | tee -a $O/round_$TAG.log
+echo "=== CLIP tower (8 f2), cascade" | tee -a $O/round_$TAG.log
+timeout 600 python tools/tower_bench.py --batch 32 --cpu > $O/tower_bench_$TAG.json 2> $O/tower_bench_$TAG.err
+echo "tower bench exit $?" | tee -a $O/round_$TAG.log
+cut -c1-260 $O/tower_bench_$TAG.json | tee -a $O/round_$TAG.log
+timeout 600 python tools/cascade_bench.py --batch 32 > $O/cascade_bench_$TAG.json 2> $O/cascade_bench_$TAG.err
+echo "cascade bench exit $?" | tee -a $O/round_$TAG.log
+cut -c1-420 $O/cascade_bench_$TAG.json | tee -a $O/round_$TAG.log
 if [ "$2" == "noncu" ]; then exit 0; fi
+TOW="python tools/tower_bench.py --batch 32 --steps 1 --warmup 1"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/ncu_tower_launches_$TAG.csv \
+    $TOW > $O/ncu_tower_$TAG.log 2>&1
+echo "ncu tower list exit $?" | tee -a $O/round_$TAG.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_global_tc2_kernel -s 24 -c 1 \
+    -o $O/prof_attn_plain_$TAG -f $TOW > $O/ncu_full_ap_$TAG.log 2>&1
+echo "ncu full plain attention exit $?" | tee -a $O/round_$TAG.log
 DEC="python tools/decoder_bench.py --batch 32 --steps 1 --warmup 1"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ncu_decoder_launches_$TAG.csv \
     $DEC > $O/ncu_decoder_$TAG.log 2>&1
