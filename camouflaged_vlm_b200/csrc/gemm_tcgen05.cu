@@ -660,7 +660,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     // narrow outputs (n <= 192) run the run-time-epilogue kernel with the MMA, the B box and the epilogue trimmed to
     // n_run columns.  The B box matters most: with a 256-row box over a 64-row weight matrix every k-block took 1.1 us
     // (0.5 us with the 128-row boxes of a CTA pair) however little the MMA had to do -- the time followed the number of
-    // box rows beyond the tensor, ~11 cycles per zero-filled row (decoder 3x3 convolutions, profiles/decoder_bench_r1x.json).
+    // box rows beyond the tensor, ~11 cycles per zero-filled row (decoder 3x3 convolutions).
     // The 5-D window boxes of the attention kernel show no such cost (tools/win_oob_probe.py).
     const int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
     const int b_box = pair ? n_run / 2 : n_run;
