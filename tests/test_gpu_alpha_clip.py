@@ -97,3 +97,23 @@ def test_tower_rejects_bad_inputs():
         bad = ac.VisionTransformer_MaPLe(56, 14, 128, 2, 8, 32, design_details={"maple_length": 2}).cuda()
         with torch.no_grad():
             bad(torch.zeros(1, 3, 56, 56).cuda(), torch.zeros(1, 1, 56, 56).cuda(), torch.zeros(2, 128).cuda(), [])
+
+
+def test_tower_repacks_after_load_state_dict():
+    cfg = aco.SMALL_HD64
+    m, sd = build(cfg, seed=0)
+    shared, deep = aco.seeded_prompts(cfg, depth=2)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 3, cfg.input_resolution, cfg.input_resolution, generator=gen).cuda()
+    al = torch.ones(1, 1, cfg.input_resolution, cfg.input_resolution).cuda()
+    call = lambda mod: mod(x, al, shared.cuda(), [d.cuda() for d in deep])
+    with torch.no_grad():
+        a = call(m).clone()
+        m.load_state_dict(aco.seeded_vit_state(cfg, 7), strict=True)        # must invalidate the packed copies
+        b = call(m).clone()
+        m.load_state_dict(sd, strict=True)
+        c = call(m)
+        import copy
+        twin = copy.deepcopy(m)
+        d = call(twin)
+    assert rel_l2(b, a) > 1e-2 and torch.equal(a, c) and torch.equal(a, d)

@@ -186,3 +186,18 @@ def test_decoder_edge_geometries(g, nc, batch):
         assert rel_l2(edge[b:b + 1].cpu(), want["edge"]) < TOL
         assert rel_l2(dec.last_hs[b:b + 1].cpu(), want["hs"]) < 3e-3
         assert float((iou[b:b + 1].cpu() - want["iou"][:, 1:]).abs().max()) < 1e-3
+
+
+def test_decoder_repacks_after_load_state_dict():
+    dec, sd = build(0)
+    emb = torch.randn(1, 256, 16, 16, generator=torch.Generator().manual_seed(9))
+    a = run(dec, sd, emb)[0].clone()
+    sd9 = mdo.seeded_decoder_state(9)
+    dec.load_state_dict({k: v for k, v in sd9.items() if not k.startswith("probe.")}, strict=True)     # must invalidate the packed copies
+    b = run(dec, sd, emb)[0].clone()
+    dec.load_state_dict({k: v for k, v in sd.items() if not k.startswith("probe.")}, strict=True)
+    c = run(dec, sd, emb)[0]
+    assert rel_l2(b, a) > 1e-2 and torch.equal(a, c)
+    import copy
+    twin = copy.deepcopy(dec)                                                                           # owns its own native handle
+    assert torch.equal(run(twin, sd, emb)[0], a)
