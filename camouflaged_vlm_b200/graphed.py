@@ -40,3 +40,38 @@ class GraphedEncoder:
         self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedCall:
+    """CUDA-graph replay of any of this package's forward calls for fixed shapes (the mask decoder's 37 launches, the
+    CLIP tower's 183): ``GraphedCall(fn, *example_tensors)`` runs ``fn(*static_copies)`` once to warm up, captures it, and
+    ``__call__(*tensors)`` copies the arguments into the static inputs and replays.  Non-tensor arguments are baked in.
+    Outputs are the graph's static tensors, overwritten by the next call; parameters must not change after capture."""
+
+    def __init__(self, fn, *example):
+        tensors = [a for a in example if isinstance(a, torch.Tensor)]
+        if not tensors or any(not t.is_cuda for t in tensors):
+            raise RuntimeError("GraphedCall needs CUDA tensor arguments")
+        dev = tensors[0].device
+        self.fn = fn
+        self.static_in = [a.clone() if isinstance(a, torch.Tensor) else a for a in example]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            fn(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = fn(*self.static_in)
+
+    @torch.no_grad()
+    def __call__(self, *args):
+        if len(args) != len(self.static_in):
+            raise ValueError(f"captured with {len(self.static_in)} arguments, got {len(args)}")
+        for s, a in zip(self.static_in, args):
+            if isinstance(s, torch.Tensor):
+                if tuple(s.shape) != tuple(a.shape) or s.dtype != a.dtype:
+                    raise ValueError(f"captured for {tuple(s.shape)} {s.dtype}, got {tuple(a.shape)} {a.dtype}")
+                s.copy_(a, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

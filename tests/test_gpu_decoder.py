@@ -201,3 +201,37 @@ def test_decoder_repacks_after_load_state_dict():
     import copy
     twin = copy.deepcopy(dec)                                                                           # owns its own native handle
     assert torch.equal(run(twin, sd, emb)[0], a)
+
+
+def test_graphed_decoder_and_tower_replay_bit_identical():
+    from camouflaged_vlm_b200.graphed import GraphedCall
+    from camouflaged_vlm_b200 import alpha_clip as ac
+    from oracle import alpha_clip_oracle as aco
+    dec, sd = build(0)
+    gen = torch.Generator().manual_seed(31)
+    emb = [torch.randn(1, 256, 16, 16, generator=gen).cuda() for _ in range(2)]
+    sparse = [torch.randn(1, 2, 256, generator=gen).cuda() for _ in range(2)]
+    pe = mdo.dense_pe(sd, 16).cuda()
+    dense = sd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(1, -1, 16, 16).contiguous().cuda()
+    fn = lambda e, s: dec(e, [], pe, s, dense, False)
+    g = GraphedCall(fn, emb[0], sparse[0])
+    for e, s in zip(emb, sparse):
+        with torch.no_grad():
+            want = fn(e, s)
+        got = g(e, s)
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+    cfg = aco.SMALL_HD64
+    tw = ac.VisionTransformer_MaPLe(cfg.input_resolution, cfg.patch_size, cfg.width, cfg.layers, cfg.heads, cfg.output_dim,
+                                    design_details={"maple_length": cfg.n_ctx}).eval()
+    tw.load_state_dict(aco.seeded_vit_state(cfg, 0), strict=True)
+    tw = tw.cuda()
+    shared, deep = aco.seeded_prompts(cfg, depth=3)
+    shared, deep = shared.cuda(), [d.cuda() for d in deep]
+    x = [torch.randn(1, 3, cfg.input_resolution, cfg.input_resolution, generator=gen).cuda() for _ in range(2)]
+    al = torch.ones(1, 1, cfg.input_resolution, cfg.input_resolution).cuda()
+    tfn = lambda xi, ai: tw(xi, ai, shared, deep)
+    tg = GraphedCall(tfn, x[0], al)
+    for xi in x:
+        with torch.no_grad():
+            want = tfn(xi, al)
+        assert torch.equal(tg(xi, al), want)
