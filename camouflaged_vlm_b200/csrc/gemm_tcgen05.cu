@@ -204,7 +204,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 const int bidx = (FEAT & F_RARE) ? tile / ep.tiles_per_batch : 0, tl = tile - bidx * ep.tiles_per_batch;
                 const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM;
                 // PAIR: each CTA stages its half of the B rows the instruction reads (n_run / 2 of them)
-                const int n0 = (tl % tiles_n) * BN + (PAIR ? cta_rank * (((FEAT & F_RARE) ? ep.n_run : BN) / 2) : 0);
+                const int n0 = (tl % tiles_n) * ((FEAT & F_RARE) ? ep.n_run : BN) + (PAIR ? cta_rank * (((FEAT & F_RARE) ? ep.n_run : BN) / 2) : 0);
                 const int bk = (FEAT & F_RARE) ? bidx * ep.b_k_off : 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -295,7 +295,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
         for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++iter) {
             const int acc = iter & 1;
             const int bidx = (FEAT & F_RARE) ? tile / ep.tiles_per_batch : 0, tl = tile - bidx * ep.tiles_per_batch;
-            const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM, n0 = (tl % tiles_n) * BN;
+            const int m0 = (tl / tiles_n) * TILE_M + cta_rank * BM, n0 = (tl % tiles_n) * ((FEAT & F_RARE) ? ep.n_run : BN);
             const int row_base = m0 + quad * 32;
             const long long brow = (FEAT & F_RARE) ? bidx * ep.batch_rows : 0;   // first output row of this batch entry
             // LayerNorm of the A rows, applied to the accumulator (GemmArgs::ln_stat): this lane's 4 rows of the
@@ -662,7 +662,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     // (0.5 us with the 128-row boxes of a CTA pair) however little the MMA had to do -- the time followed the number of
     // box rows beyond the tensor, ~11 cycles per zero-filled row (decoder 3x3 convolutions).
     // The 5-D window boxes of the attention kernel show no such cost (tools/win_oob_probe.py).
-    const int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
+    int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
+    // few tiles (small m: the batch-1 latency path of the CLIP tower and the decoder): a narrower N tile, run by the same
+    // run-time kernel, puts more SMs to work (m = 579, n = 1024: 20 tiles of 256 columns -> 80 of 64)
+    if (n_run == BN && !pair && !a.stat_out && !a.ln_rows && nbatch == 1 && !(mode && mode[0] == '1')) {
+        const long long tm = (a.m + BM - 1) / BM;
+        if (tm * ((a.n + BN - 1) / BN) * 2 <= num_sms()) {
+            n_run = 128;
+            if (tm * ((a.n + 127) / 128) * 2 <= num_sms()) n_run = 64;
+        }
+    }
     const int b_box = pair ? n_run / 2 : n_run;
     CUtensorMap tA1, tB1, tA2, tB2;
     if (a.conv_pitch > 0 && (a.k1 != 9 * BK || a.k2 > 0 || nbatch > 1 || a.lda1 != BK || a.ln_rows))
@@ -696,7 +705,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
                reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
                a.act_abs, a.conv_pitch, n_run};
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
-    const int tiles_n = (a.n + BN - 1) / BN;
+    const int tiles_n = (a.n + n_run - 1) / n_run;      // n_run == BN except for narrow outputs / few-tile problems
     const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;
     ep.tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = nbatch * tiles_m * tiles_n;

@@ -276,3 +276,23 @@ def test_attention_plain(batch, tokens, heads, hd):
     out = torch.full((batch * tokens + 256, d), 7.0, device=DEV, dtype=torch.bfloat16)
     _lib.check(_lib.load().cvlm_op_attention_plain(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, hd, _lib.stream_ptr()))
     assert torch.equal(out[:batch * tokens].float(), got) and bool((out[batch * tokens:] == 7.0).all())
+
+
+@pytest.mark.parametrize("m,n,k", [(579, 1024, 1024), (579, 1024, 4096), (579, 3072, 1024), (1737, 1024, 1024), (130, 520, 200),
+                                   (64, 4096, 1024), (1, 776, 64)])
+def test_gemm_few_tiles_narrow_n(m, n, k, monkeypatch):
+    """Small-M problems (the batch-1 latency path) are cut into 128- or 64-column tiles by the launcher so that more SMs
+    work; every epilogue must give the same numbers as the 256-column kernels, bit for bit (same K order per element)."""
+    monkeypatch.delenv("CVLM_GEMM_MODE", raising=False)
+    a = _randn(m, k, seed=500 + m, dtype=torch.bfloat16)
+    b = _randn(n, k, seed=600 + n, dtype=torch.bfloat16, scale=0.05)
+    bias = _randn(n, seed=700 + k)
+    res = _randn(m, n, seed=800 + k)
+    want = a.float() @ b.float().t() + bias
+    got = ops.gemm_bf16(a, b, bias=bias, residual=res)
+    assert _rel(got, want + res) < 2e-5
+    got16 = ops.gemm_bf16(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16)
+    assert _rel(got16.float(), torch.nn.functional.gelu(want)) < 4e-3
+    monkeypatch.setenv("CVLM_GEMM_MODE", "1cta")          # the 256-column kernel on the same problem
+    assert torch.equal(ops.gemm_bf16(a, b, bias=bias, residual=res), got)
+    assert torch.equal(ops.gemm_bf16(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16), got16)
