@@ -1,14 +1,14 @@
 """Mask decoder timing on one GPU: decoder alone on resident embeddings, and the encoder -> decoder ->
 postprocess cascade.  CUDA events on the launching stream, warm-up first, inputs larger than L2 at the default batch.
-Prints one JSON line.  --cpu also times the oracle (CPU restatement of the reference decoder) on one image.
+Prints one JSON line.  The CPU baseline beside it (the oracle on the host cores) is measured by tests/cpu_baselines.py:
+only tests/, smoke() and bench.py may run anything under oracle/.
 
-    python tools/decoder_bench.py [--batch 32] [--steps 10] [--warmup 3] [--cascade] [--cpu]
+    python tools/decoder_bench.py [--batch 32] [--steps 10] [--warmup 3] [--cascade]
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -85,7 +85,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--cascade", action="store_true")
-    ap.add_argument("--cpu", action="store_true")
     args = ap.parse_args()
     B, g = args.batch, 64
     dec = seeded_decoder()
@@ -131,18 +130,6 @@ def main():
         ms_c = timed(cascade, max(3, args.steps // 2), args.warmup)
         line["cascade"] = {"encoder_ms": ms_e, "encoder_decoder_postprocess_ms": ms_c, "img_per_s": B / ms_c * 1e3,
                            "decoder_share": 1.0 - ms_e / ms_c}
-    if args.cpu:
-        from oracle import mask_decoder_oracle as mdo     # cpu_baseline leg only
-        sd = mdo.seeded_decoder_state(0)
-        e1 = emb[:1].cpu()
-        mdo.decode_all(sd, e1)
-        t0 = time.perf_counter()
-        n = 3
-        for _ in range(n):
-            mdo.binary_mask(mdo.decode_all(sd, e1)["masks"][:, 0:1], 1024)
-        dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n} images, oracle decode_all + postprocess on the host"}
     print(json.dumps(line))
 
 

@@ -4,7 +4,7 @@ TAG=${1:-d}
 O=gpurun_out
 mkdir -p $O
 timeout 600 python -m pytest -q -m gpu tests/test_gpu_decoder.py 2>&1 | tail -15 | tee $O/dec_tests_$TAG.log
-timeout 600 python tools/decoder_bench.py --batch 32 --cascade --cpu > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
+timeout 600 python tools/decoder_bench.py --batch 32 --cascade > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
 echo "bench exit $?"; tail -3 $O/decoder_bench_$TAG.err; cat $O/decoder_bench_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ncu_decoder_launches_$TAG.csv \
   python tools/decoder_bench.py --batch 32 --steps 1 --warmup 1 > $O/ncu_decoder_$TAG.log 2>&1

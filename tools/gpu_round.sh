@@ -18,11 +18,12 @@ echo "bench exit $?" | tee -a $O/round_$TAG.log
 tail -c 3000 $O/bench_$TAG.json | tee -a $O/round_$TAG.log
 tail -5 $O/bench_$TAG.err | tee -a $O/round_$TAG.log
 echo "=== mask decoder (8 f1)" | tee -a $O/round_$TAG.log
-timeout 600 python tools/decoder_bench.py --batch 32 --cascade --cpu > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
+timeout 600 python tools/decoder_bench.py --batch 32 --cascade > $O/decoder_bench_$TAG.json 2> $O/decoder_bench_$TAG.err
 echo "decoder bench exit $?" | tee -a $O/round_$TAG.log
 cut -c1-260 $O/decoder_bench_$TAG.json | tee -a $O/round_$TAG.log
+timeout 600 python tests/cpu_baselines.py $O/cpu_baselines_$TAG.json 2>&1 | tail -3 | tee -a $O/round_$TAG.log
 echo "=== CLIP tower (8 f2), cascade" | tee -a $O/round_$TAG.log
-timeout 600 python tools/tower_bench.py --batch 32 --cpu > $O/tower_bench_$TAG.json 2> $O/tower_bench_$TAG.err
+timeout 600 python tools/tower_bench.py --batch 32 > $O/tower_bench_$TAG.json 2> $O/tower_bench_$TAG.err
 echo "tower bench exit $?" | tee -a $O/round_$TAG.log
 cut -c1-260 $O/tower_bench_$TAG.json | tee -a $O/round_$TAG.log
 timeout 600 python tools/cascade_bench.py --batch 32 > $O/cascade_bench_$TAG.json 2> $O/cascade_bench_$TAG.err

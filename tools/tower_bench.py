@@ -1,14 +1,14 @@
 """Alpha-CLIP / MaPLe visual tower timing on one GPU: ViT-L/14@336 with 2 context tokens and 8 deeper
 prompts, images resident in HBM.  CUDA events on the launching stream after warm-up; the activations of a batch (> 1 GB)
-exceed L2.  Prints one JSON line; --cpu also times the oracle (CPU restatement of the reference tower) on one image.
+exceed L2.  Prints one JSON line; the CPU baseline beside it (the oracle on the host cores) is measured by
+tests/cpu_baselines.py: only tests/, smoke() and bench.py may run anything under oracle/.
 
-    python tools/tower_bench.py [--batch 32] [--steps 10] [--warmup 3] [--cpu]
+    python tools/tower_bench.py [--batch 32] [--steps 10] [--warmup 3]
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -35,7 +35,6 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cpu", action="store_true")
     args = ap.parse_args()
     B = args.batch
     m = build_tower()
@@ -72,20 +71,6 @@ def main():
                                    "pass (the cascade runs two per image)", "l2": "activations of a batch exceed L2"},
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                          "peak_source": src, "traffic": None, "flops_per_image": flops_per_image()}}
-    if args.cpu:
-        from oracle import alpha_clip_oracle as aco        # cpu_baseline leg only
-        cfg = aco.VitConfig()
-        sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
-        x1, a1 = img[:1].cpu(), alpha[:1].cpu()
-        sh, dp = shared.cpu(), [d.cpu() for d in deep]
-        aco.vit_maple_forward(sd, cfg, x1, a1, sh, dp)
-        t0 = time.perf_counter()
-        n = 3
-        for _ in range(n):
-            aco.vit_maple_forward(sd, cfg, x1, a1, sh, dp)
-        dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n} images, oracle vit_maple_forward on the host"}
     print(json.dumps(line))
 
 
