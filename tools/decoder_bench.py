@@ -59,8 +59,17 @@ def hbm_roofline(B, g, ms):
     st = algorithmic_bytes_per_image(g)
     total = sum(st.values()) * B
     ach = total / (ms * 1e-3) / 1e9
+    # measured DRAM bytes of one forward from the committed ncu capture (dram__bytes_read + write over its 38 launches)
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_decoder_traffic_r1final.json")
+    try:
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B and g == 64:
+            traffic = tj["dram_bytes_per_forward"]
+    except Exception:
+        traffic = None
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
-            "traffic": None, "algorithmic_bytes_per_image": st,
+            "traffic": traffic, "algorithmic_bytes_per_forward": total, "algorithmic_bytes_per_image": st,
             "note": "whole decoder: bytes every launch must read and write once (weights excluded) / measured time; "
                     "the token kernels and the implicit convolutions are not HBM-bound (DESIGN.md 5.6)"}
 
