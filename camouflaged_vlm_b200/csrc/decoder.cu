@@ -753,19 +753,29 @@ __global__ void __launch_bounds__(256) dec_masks_kernel(const float* __restrict_
 
 // F.interpolate(mode="bilinear", align_corners=False) on fp32 NCHW planes (postprocess_masks,
 // models/sam_maskdecoder_edge.py:380-387)
+template <int VEC>
 __global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                               int ih, int iw, int oh, int ow, float sh, float sw) {
-    // block = 64 x 4 output pixels of plane blockIdx.z
-    const int ox = blockIdx.x * 64 + (threadIdx.x & 63), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (ox >= ow || oy >= oh) return;
-    const float fy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
-    const int y0 = min(static_cast<int>(fy), ih - 1), x0 = min(static_cast<int>(fx), iw - 1);
-    const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    // block = (64 * VEC) x 4 output pixels of plane blockIdx.z; a thread writes VEC consecutive pixels of one row
+    const int ox0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * VEC, oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ox0 >= ow || oy >= oh) return;
+    const float fy = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(fy), ih - 1), y1 = min(y0 + 1, ih - 1);
+    const float ly = fy - y0, hy = 1.f - ly;
     const float* p = in + static_cast<long long>(blockIdx.z) * ih * iw;
-    out[(static_cast<long long>(blockIdx.z) * oh + oy) * ow + ox] =
-        hy * (hx * __ldg(p + y0 * iw + x0) + lx * __ldg(p + y0 * iw + x1)) +
-        ly * (hx * __ldg(p + y1 * iw + x0) + lx * __ldg(p + y1 * iw + x1));
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int ox = ox0 + j;
+        const float fx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+        const int x0 = min(static_cast<int>(fx), iw - 1), x1 = min(x0 + 1, iw - 1);
+        const float lx = fx - x0, hx = 1.f - lx;
+        v[j] = hy * (hx * __ldg(p + y0 * iw + x0) + lx * __ldg(p + y0 * iw + x1)) +
+               ly * (hx * __ldg(p + y1 * iw + x0) + lx * __ldg(p + y1 * iw + x1));
+    }
+    float* o = out + (static_cast<long long>(blockIdx.z) * oh + oy) * ow + ox0;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else o[0] = v[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1144,8 +1154,13 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
 int bilinear_resize_launch(const float* in, float* out, long long planes, int ih, int iw, int oh, int ow, cudaStream_t stream) {
     if (!in || !out || planes < 1 || ih < 1 || iw < 1 || oh < 1 || ow < 1) return set_error(CVLM_ERR_ARG, "bilinear_resize: bad arguments");
     if (planes > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "bilinear_resize: more than 65535 planes in one call");
-    bilinear_resize_kernel<<<dim3((ow + 63) / 64, (oh + 3) / 4, static_cast<unsigned>(planes)), 256, 0, stream>>>(
-        in, out, ih, iw, oh, ow, static_cast<float>(ih) / oh, static_cast<float>(iw) / ow);
+    const float sh = static_cast<float>(ih) / oh, sw = static_cast<float>(iw) / ow;
+    if (ow % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        bilinear_resize_kernel<4><<<dim3((ow + 255) / 256, (oh + 3) / 4, static_cast<unsigned>(planes)), 256, 0, stream>>>(
+            in, out, ih, iw, oh, ow, sh, sw);
+    else
+        bilinear_resize_kernel<1><<<dim3((ow + 63) / 64, (oh + 3) / 4, static_cast<unsigned>(planes)), 256, 0, stream>>>(
+            in, out, ih, iw, oh, ow, sh, sw);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
