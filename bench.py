@@ -46,16 +46,28 @@ def parse_args():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-decoder", action="store_true", help="skip the mask-decoder / cascade / CLIP-tower legs (SURVEY 8 f1, f2)")
+    ap.add_argument("--skip-torch-gpu-baseline", action="store_true",
+                    help="skip the leg that times the reference module itself (eager PyTorch) on this GPU")
+    ap.add_argument("--skip-train", action="store_true", help="skip the adapter-training step leg (SURVEY 8 f4)")
+    ap.add_argument("--total-batch", type=int, default=0,
+                    help="strong scaling (BASELINE.json configs[2]): this many images in total, split over the ranks and "
+                         "processed in micro-batches of --batch; 0 = weak scaling (--batch images per GPU per step)")
+    ap.add_argument("--gather-dtype", choices=["fp32", "bf16"], default="fp32",
+                    help="payload of the N>1 embedding all-gather (bf16 halves the bytes, adds ~1.1e-3 rel-L2)")
     return ap.parse_args()
 
 
 def workload_config(args, cfg, world):
+    per_rank = args.total_batch // world if args.total_batch else args.batch
     return {
-        "workload": f"SAM {args.model} ImageEncoderViT forward (interm={not args.no_interm}), bf16, batch "
-                    f"{args.batch} per GPU, {cfg.img_size}x{cfg.img_size} synthetic images, random-init weights "
-                    "(BASELINE.json configs[1]; configs[2] sharding at N>1)",
-        "batch_per_gpu": args.batch,
-        "global_batch": args.batch * world,
+        "workload": f"SAM {args.model} ImageEncoderViT forward (interm={not args.no_interm}), bf16, "
+                    + (f"{args.total_batch} images per step in total ({per_rank} per GPU in micro-batches of {args.batch}), "
+                       if args.total_batch else f"batch {args.batch} per GPU, ")
+                    + f"{cfg.img_size}x{cfg.img_size} synthetic images, random-init weights "
+                    "(BASELINE.json configs[1]; configs[2] sharding + embedding all-gather at N>1)",
+        "batch_per_gpu": per_rank,
+        "micro_batch": args.batch,
+        "global_batch": per_rank * world,
         "img_size": cfg.img_size,
         "parallelism": f"dp{world} (batch-sharded, weights replicated)",
         "l2": "inputs larger than L2: 12.6 MB/image input, ~85 MB/image of activations streamed per block",
@@ -141,32 +153,48 @@ def gemm_flops_per_image(cfg):
 
 
 # ----------------------------------------------------------------------------------------------
-def time_oracle_cpu(cfg, sd_cpu, steps, warmup, budget_s=240.0):
-    """One image per step on all host threads.  Returns (img/s, seconds per step, steps run, warmups run)."""
+def cpu_reference_forward(cfg, sd_cpu):
+    """The reference's CPU implementation of the path as a callable x -> (embedding, interm list), and its kind:
+    "reference" = the reference's own ImageEncoderViT module from oracle/_ref/refsam (staged, unmodified, by
+    oracle/stage_ref.py), "port" = the oracle restatement when nothing is staged."""
+    from oracle import ref_import
+    if ref_import.staged_encoder_available():
+        ref = ref_import.build_reference_encoder(cfg, staged=True).eval()
+        ref.load_state_dict(sd_cpu, strict=True)
+        return (lambda x: ref(x, interm=True)), "reference"
+    from oracle import encoder_oracle as orc
+    return (lambda x: orc.encoder_forward(sd_cpu, cfg, x, interm=True)), "port"
+
+
+def time_reference_cpu(cfg, sd_cpu, steps, warmup, budget_s=240.0):
+    """One image per step on all host threads.  Returns a dict: img/s, seconds per step, steps / warm-ups actually run
+    (capped to the budget), the kind of implementation timed, and the last embedding (for the parity line)."""
     import torch
     from camouflaged_vlm_b200.synth import seeded_images
-    from oracle import encoder_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
+    fwd, kind = cpu_reference_forward(cfg, sd_cpu)
     x = seeded_images(cfg, 1, 0)
     t0 = time.perf_counter()
-    orc.encoder_forward(sd_cpu, cfg, x, interm=True)          # first pass doubles as warm-up / calibration
+    out = fwd(x)[0]                                           # first pass doubles as warm-up / calibration
     first = time.perf_counter() - t0
     warm_done = 1
     while warm_done < warmup and (warm_done + 1 + max(1, steps)) * first < budget_s:
-        orc.encoder_forward(sd_cpu, cfg, x, interm=True)
+        fwd(x)
         warm_done += 1
     steps_run = max(1, min(steps, int((budget_s - warm_done * first) / max(first, 1e-9))))
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps_run):
-        orc.encoder_forward(sd_cpu, cfg, x, interm=True)
-    dt = (time.perf_counter() - t0) / steps_run
-    return 1.0 / dt, dt, steps_run, warm_done
+        t0 = time.perf_counter()
+        out = fwd(x)[0]
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"ips": 1.0 / dt, "dt": dt, "best_dt": min(times), "steps": steps_run, "warmup": warm_done, "kind": kind,
+            "out": out, "image": "seeded_images(cfg, 1, 0)[0]"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores.
-    The reference is Python/torch and cannot travel to the GPU box (no /root/reference there), so this
-    arm times the oracle port (oracle/encoder_oracle.py, pinned to the reference's outputs)."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores -- the reference
+    module itself from oracle/_ref/refsam when staged (oracle/stage_ref.py), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
@@ -177,20 +205,75 @@ def run_reference(args):
     cfg = PRESETS[args.model]
     sd = seeded_state_dict(cfg, 0)
     with torch.no_grad():
-        ips, dt, steps_run, warm_run = time_oracle_cpu(cfg, sd, args.steps, args.warmup)
+        r = time_reference_cpu(cfg, sd, args.steps, max(args.warmup, 1))
     cores = os.cpu_count() or 1
+    what = ("the reference's ImageEncoderViT module (oracle/_ref/refsam, unmodified)" if r["kind"] == "reference"
+            else "oracle port of the reference (nothing staged under oracle/_ref)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": steps_run,
-        "warmup": warm_run, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": r["ips"], "unit": UNIT, "n_gpus": world, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": r["dt"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, world),
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1 image per step (a batch-32 step is 32 independent images; the CPU rate is per image), "
-                                   f"{steps_run} timed steps after {warm_run} warm-up (requested {args.steps}/{args.warmup}, "
-                                   "capped to a 4-minute budget)"},
-        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": r["ips"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+                         "sample": f"{what}, fp32, torch {torch.__version__}, {cores} threads: 1 image per step (a batch-32 "
+                                   f"step is 32 independent images; the CPU rate is per image), {r['steps']} timed steps "
+                                   f"after {r['warmup']} warm-up (requested {args.steps}/{args.warmup}, capped to a "
+                                   f"4-minute budget), best step {r['best_dt']:.2f} s"},
+        "e2e": {"value": r["ips"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_torch_gpu_baseline(cfg, sd_cpu, dev, ours, batches=(16, 8, 4)):
+    """SURVEY 2.2 / BASELINE.md: "the bar on B200 is eager PyTorch + cuBLAS on the same box".  The reference module
+    itself (oracle/_ref/refsam) moved to the GPU, stock code path: fp32 eager and under torch.autocast(bf16), at the
+    largest batch of `batches` that fits (it materialises 32 prompt tensors and the [B*16, 4096, 4096] fp32 scores),
+    next to this repository's encoder on the same images.  A baseline, never the product."""
+    import torch
+    from camouflaged_vlm_b200.synth import seeded_images
+    from oracle import ref_import
+    from oracle.encoder_oracle import rel_l2
+    if not ref_import.staged_encoder_available():
+        return {"unavailable": "no staged reference under oracle/_ref (run oracle/stage_ref.py in the container)"}
+    ref = ref_import.build_reference_encoder(cfg, staged=True).eval()
+    ref.load_state_dict(sd_cpu, strict=True)
+    ref = ref.to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    rep = None
+    for B in batches:
+        try:
+            x = seeded_images(cfg, B, 0).to(dev)
+            with torch.no_grad():
+                y32 = ref(x, interm=True)[0]
+                ms32 = timeit(lambda: ref(x, interm=True), 2)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y16 = ref(x, interm=True)[0].float()
+                    ms16 = timeit(lambda: ref(x, interm=True), 3)
+                yo = ours(x)
+                mso = timeit(lambda: ours(x), 5)
+            rep = {"batch": B, "what": "the reference ImageEncoderViT module (oracle/_ref/refsam, unmodified) on this GPU, "
+                                       "forward(x, interm=True), same weights and images",
+                   "torch_fp32_eager": {"img_per_s": B / ms32 * 1e3, "ms": ms32},
+                   "torch_autocast_bf16": {"img_per_s": B / ms16 * 1e3, "ms": ms16, "rel_l2_vs_fp32": rel_l2(y16, y32)},
+                   "ours_same_batch": {"img_per_s": B / mso * 1e3, "ms": mso, "rel_l2_vs_fp32": rel_l2(yo, y32)}}
+            break
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            continue
+    del ref
+    torch.cuda.empty_cache()
+    return rep or {"unavailable": f"out of memory at every batch of {batches}"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -198,6 +281,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from camouflaged_vlm_b200 import PRESETS, _lib, build_encoder
+    from camouflaged_vlm_b200.dist import ChunkGatherer
     from camouflaged_vlm_b200.synth import param_shapes
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +296,16 @@ def run_ours(args):
     cfg = PRESETS[args.model]
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     interm = not args.no_interm
+    # weak scaling (default): B images per GPU per step.  Strong scaling (--total-batch T, BASELINE.json configs[2]):
+    # T images per step in total, T / world per rank, encoded in micro-batches of B.
+    if args.total_batch:
+        if args.total_batch % (world * B):
+            raise SystemExit(f"--total-batch {args.total_batch} must be a multiple of world * batch = {world * B}")
+        per_rank = args.total_batch // world
+    else:
+        per_rank = B
+    n_micro = per_rank // B
+    gdtype = torch.bfloat16 if args.gather_dtype == "bf16" else torch.float32
 
     # random-init weights of the architecture (same recipe as synth.seeded_state_dict, generated on the GPU)
     model = build_encoder(cfg).eval().to(dev)
@@ -223,10 +317,27 @@ def run_ours(args):
                 p.add_(1.0)
     assert set(dict(model.named_parameters())) == set(param_shapes(cfg))
     x_dev = torch.randn(B, cfg.in_chans, cfg.img_size, cfg.img_size, generator=gen, device=dev)
+    tail = (cfg.out_chans, cfg.grid, cfg.grid)
+    # N > 1: the embeddings of every micro-batch are all-gathered on a side stream underneath the encoder of the next
+    # one (two result buffers alternate), and the timed region ends when the last gather has landed -- the exchange
+    # step of configs[2] is INSIDE `value`
+    gatherers = [ChunkGatherer(B, tail, dev, gdtype) for _ in range(2)] if world > 1 else None
+    micro_done = [0]
 
     def step(x):
-        with torch.no_grad():
-            return model(x, interm=interm)
+        for _ in range(n_micro):
+            with torch.no_grad():
+                res = model(x, interm=interm)
+            if gatherers is not None:
+                emb = res[0] if interm else res
+                g = gatherers[micro_done[0] % 2]
+                g.submit(0, B, emb)
+                micro_done[0] += 1
+
+    def drain():
+        if gatherers is not None:
+            for g in gatherers:
+                g.finish()
 
     def barrier():
         if world > 1:
@@ -242,6 +353,7 @@ def run_ours(args):
 
     for _ in range(W):
         step(x_dev)
+    drain()
     barrier()
 
     # ---- timed region: inputs resident in HBM
@@ -252,18 +364,30 @@ def run_ours(args):
     e0.record()
     for _ in range(K):
         step(x_dev)
+    drain()
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = model.last_launch_count * K
-    value = world * B * K / (ms_total * 1e-3)
+    launches = model.last_launch_count * K * n_micro
+    value = world * per_rank * K / (ms_total * 1e-3)
+    gather_info = None
+    if gatherers is not None:
+        gather_info = {"inside_value": True, "dtype": args.gather_dtype, "bytes_received_per_rank_per_step":
+                       (world - 1) * per_rank * tail[0] * tail[1] * tail[2] * (2 if gdtype == torch.bfloat16 else 4),
+                       "how": "dist.ChunkGatherer: all_gather of each micro-batch's embeddings on a side stream under the "
+                              "next micro-batch's encoder; the timed region waits for the last one"}
+    gatherers = None
+
+    def plain_step(x):
+        with torch.no_grad():
+            return model(x, interm=interm)
 
     # ---- per-kernel CUDA-event timing over the same K steps (events bracket every launch on the stream)
     lib = _lib.load()
     lib.cvlm_encoder_set_profiling(model._handle, 1)
     for _ in range(K):
-        step(x_dev)
+        plain_step(x_dev)
     torch.cuda.synchronize()
     import ctypes as C
     ms_kind = (C.c_float * len(_lib.PROF_KINDS))()
@@ -275,7 +399,7 @@ def run_ours(args):
     gemm_launches = sum(kernels[k]["launches_per_step"] for k in _lib.PROF_KINDS if k.startswith("gemm"))
     peaks = load_peaks()
     gemm_tflops = B * gemm_flops_per_image(cfg) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    step_tflops = B * cfg.flops_per_image() / (ms_total / K * 1e-3) / 1e12
+    step_tflops = per_rank * cfg.flops_per_image() / (ms_total / K * 1e-3) / 1e12
     # DRAM traffic per GEMM launch from the committed `ncu --set full` capture of this kernel (same batch)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_gemm_latest.json")
@@ -294,7 +418,7 @@ def run_ours(args):
                         "launch are in DESIGN.md section 5",
         "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
         "launches_per_step": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
-        "share_of_step": gemm_ms / (ms_total / K),
+        "share_of_step": gemm_ms * n_micro / (ms_total / K),
         "whole_step": {"achieved_tflops": step_tflops, "frac_of_sustained": step_tflops / peaks["sustained"],
                        "frac_of_burst": step_tflops / peaks["burst"], "frac_of_nominal_2250": step_tflops / 2250.0,
                        "flops_per_image": cfg.flops_per_image()},
@@ -306,31 +430,45 @@ def run_ours(args):
         x_host = torch.empty(B, cfg.in_chans, cfg.img_size, cfg.img_size, pin_memory=True)
         x_host.copy_(x_dev)
         out_host = torch.empty(B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
-        gathered = torch.empty(world * B, cfg.out_chans, cfg.grid, cfg.grid, device=dev) if world > 1 else None
+        CH = 8
+        e2e_gather = [ChunkGatherer(B, tail, dev, gdtype) for _ in range(2)] if world > 1 else None
+        e2e_calls = [0]
 
         def e2e_step():
             # the public host-buffer call: chunked H2D on a copy stream under the encoder, D2H of this rank's
-            # embeddings per chunk; at N > 1 the embeddings are also all-gathered on the devices (configs[2])
-            with torch.no_grad():
-                res = model.forward_host(x_host, out_host=out_host, chunk=8, interm=interm, return_device=world > 1)
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered, res[1])
+            # embeddings per chunk; at N > 1 each chunk's embeddings are also all-gathered on the devices (configs[2])
+            # on a side stream under the next chunk's encoder
+            for _ in range(n_micro):
+                g = e2e_gather[e2e_calls[0] % 2] if e2e_gather is not None else None
+                e2e_calls[0] += 1
+                with torch.no_grad():
+                    model.forward_host(x_host, out_host=out_host, chunk=CH, interm=interm,
+                                       on_chunk=g.submit if g is not None else None)
+
+        def e2e_drain():
+            if e2e_gather is not None:
+                for g in e2e_gather:
+                    g.finish()
 
         e2e_step()
+        e2e_drain()
         barrier()
         e0.record()
         for _ in range(K):
             e2e_step()
+        e2e_drain()
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-        e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": world * x_host.numel() * 4, "d2h_bytes_per_step": world * out_host.numel() * 4,
-               "ms_per_step": ms_e2e / K,
-               "note": "ImageEncoderViT.forward_host: pinned host -> device in chunks of 8 on a copy stream under "
+        e2e = {"value": world * per_rank * K / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": world * n_micro * x_host.numel() * 4,
+               "d2h_bytes_per_step": world * n_micro * out_host.numel() * 4, "ms_per_step": ms_e2e / K,
+               "note": f"ImageEncoderViT.forward_host: pinned host -> device in chunks of {CH} on a copy stream under "
                        "forward(x, interm) of the previous chunk, "
-                       + ("NCCL all_gather_into_tensor of the embeddings, " if world > 1 else "")
+                       + (f"all-gather ({args.gather_dtype}) of each chunk's embeddings on a side stream under the next "
+                          "chunk's encoder (dist.ChunkGatherer), " if world > 1 else "")
                        + "device -> pinned host copy of each rank's embeddings (per chunk, same copy stream); whole-job bytes"}
+        e2e_gather = None
 
     # ---- the next row of the hot path: the mask decoder on this step's embeddings, and the
     # encoder -> decoder -> postprocess cascade; reported beside the headline, not part of it
@@ -409,23 +547,41 @@ def run_ours(args):
         del tw
         torch.cuda.empty_cache()
 
-    # ---- CPU baseline beside it (rank 0, single-GPU run only)
+    # ---- CPU baseline beside it (rank 0, single-GPU run only): the reference module itself (oracle/_ref/refsam) when
+    # staged, else the oracle port, with THIS run's weights; its embedding of the timed image is kept and compared with
+    # the CUDA encoder's on the same image -> `parity` (north_star: rel-L2 <= 1e-2)
     cpu = None
+    parity = None
+    tgb = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        from camouflaged_vlm_b200.synth import seeded_images
+        from oracle.encoder_oracle import rel_l2
         sd_cpu = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
         with torch.no_grad():
-            ips, dt, steps_run, _ = time_oracle_cpu(cfg, sd_cpu, 1, 1, budget_s=90.0)
-        cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"oracle (CPU restatement of the reference, fp32, torch {torch.__version__}) on 1 image of the "
-                         f"same workload, {steps_run} timed pass after 1 warm-up, {dt:.1f} s per image"}
+            r = time_reference_cpu(cfg, sd_cpu, 3, 1, budget_s=150.0)
+            ours1 = model(seeded_images(cfg, 1, 0).to(dev)).cpu()
+        what = ("the reference ImageEncoderViT module (oracle/_ref/refsam, unmodified)" if r["kind"] == "reference"
+                else "oracle port of the reference")
+        cpu = {"value": r["ips"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": r["kind"],
+               "sample": f"{what}, fp32, torch {torch.__version__}, on 1 image of the same workload with this run's "
+                         f"weights: {r['steps']} timed passes after {r['warmup']} warm-up, mean {r['dt']:.2f} s "
+                         f"(best {r['best_dt']:.2f} s) per image"}
+        parity = {"rel_l2": rel_l2(ours1, r["out"]), "gate": 1e-2, "image": r["image"], "weights_seed": 1234,
+                  "against": r["kind"] + " (CPU fp32) embedding of the same image with the same weights"}
+        if not args.skip_torch_gpu_baseline and args.model == "vit_h":
+            def ours_fn(x):
+                return model(x, interm=True)[0]
+            tgb = time_torch_gpu_baseline(cfg, sd_cpu, dev, ours_fn)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if args.total_batch else "weak",
+            "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels, "mask_decoder": f1, "alpha_clip_tower": f2,
+            "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgb, "gather": gather_info,
+            "kernels": kernels, "mask_decoder": f1, "alpha_clip_tower": f2,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -68,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _SIGS = {
     "cvlm_last_error": (C.c_char_p, []),
     "cvlm_abi_version": (C.c_int, []),
+    "cvlm_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "cvlm_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "cvlm_encoder_create": (C.c_int, [C.POINTER(EncoderConfigC), C.POINTER(C.c_void_p)]),
     "cvlm_encoder_destroy": (C.c_int, [C.c_void_p]),
     "cvlm_encoder_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
@@ -152,6 +154,24 @@ def check(rc: int, what: str = "") -> int:
     return rc
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream ON `device` (the tensors' device, not the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t):
+    """Context manager: make the tensor's device current for a C-ABI call (function attributes, per-device caches and
+    the kernel launches all follow the CUDA current device)."""
+    import torch
+    return torch.cuda.device(t.device)
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().cvlm_set_option(name.encode(), int(value)), f"cvlm_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    check(load().cvlm_get_option(name.encode(), C.byref(v)), f"cvlm_get_option({name})")
+    return v.value

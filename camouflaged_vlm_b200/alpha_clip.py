@@ -112,6 +112,15 @@ class VisionTransformer_MaPLe(nn.Module):
         except Exception:
             pass
 
+    def _weights_key(self, device):
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _get_workspace(self, need: int, dev) -> torch.Tensor:
+        # a CUDA graph that captured the old buffer keeps its own reference (graphed.py), so replacing is safe
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._workspace
+
     def _ensure_ready(self, device) -> int:
         lib = _lib.load()
         if self._handle is None:
@@ -122,7 +131,7 @@ class VisionTransformer_MaPLe(nn.Module):
             h = C.c_void_p()
             _lib.check(lib.cvlm_vit_create(C.byref(cc), C.byref(h)), "cvlm_vit_create")
             self._handle = h.value
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = self._weights_key(device)
         if self._packed is None or self._packed_key != key:
             self._packed = pack_vit_weights(dict(self.state_dict()), self._layers, device)
             for name, t in self._packed.items():
@@ -137,13 +146,17 @@ class VisionTransformer_MaPLe(nn.Module):
             raise NotImplementedError("return_attn=True is not implemented by the B200 tower")
         if not x.is_cuda:
             raise RuntimeError("VisionTransformer_MaPLe (B200) needs CUDA tensors: there is no CPU path")
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or shared_ctx.requires_grad):
-            raise RuntimeError("VisionTransformer_MaPLe (B200) is inference only; call it under torch.no_grad()")
         B, R = x.shape[0], self.input_resolution
         if tuple(x.shape[1:]) != (3, R, R) or alpha is None or tuple(alpha.shape) != (B, 1, R, R):
             raise ValueError(f"expected images [B,3,{R},{R}] and alpha [B,1,{R},{R}]")
         if shared_ctx is None or tuple(shared_ctx.shape) != (self._n_ctx, self._width):
             raise ValueError(f"shared_ctx must be [{self._n_ctx},{self._width}]")
+        if torch.is_grad_enabled() and (x.requires_grad or alpha.requires_grad or shared_ctx.requires_grad or
+                                        any(d.requires_grad for d in (compound_deeper_prompts or []))):
+            # parameters that merely have requires_grad=True (the default of a freshly built module) do not block an
+            # inference call; a differentiable INPUT does, because no gradient would reach it
+            raise RuntimeError("VisionTransformer_MaPLe (B200) is inference only: an input requires grad; detach it or "
+                               "call under torch.no_grad()")
         dev = x.device
         deep = list(compound_deeper_prompts or [])
         img = x.detach().float().contiguous()
@@ -159,13 +172,12 @@ class VisionTransformer_MaPLe(nn.Module):
         for s in range(0, B, self.max_chunk):
             e = min(B, s + self.max_chunk)
             need = _lib.check(lib.cvlm_vit_workspace_bytes(h, e - s), "cvlm_vit_workspace_bytes")
-            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-                self._workspace = None
-                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-            _lib.check(lib.cvlm_vit_forward(h, img[s:e].data_ptr(), alp[s:e].data_ptr(), ctx.data_ptr(),
-                                            deep_t.data_ptr() if deep_t is not None else None, len(deep), e - s,
-                                            out[s:e].data_ptr(), self._workspace.data_ptr(), self._workspace.numel(),
-                                            _lib.stream_ptr()), "cvlm_vit_forward")
+            ws = self._get_workspace(need, dev)
+            with torch.cuda.device(dev):        # the C ABI launches on the CUDA current device
+                _lib.check(lib.cvlm_vit_forward(h, img[s:e].data_ptr(), alp[s:e].data_ptr(), ctx.data_ptr(),
+                                                deep_t.data_ptr() if deep_t is not None else None, len(deep), e - s,
+                                                out[s:e].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.stream_ptr(dev)), "cvlm_vit_forward")
             launches += lib.cvlm_vit_last_launches(h)
         self.last_launch_count = launches
         return out.to(x.dtype) if x.dtype in (torch.float16, torch.bfloat16) else out

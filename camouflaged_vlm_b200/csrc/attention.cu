@@ -421,8 +421,8 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     if (static_cast<long long>(batch) * p.nW * p.nW > 65535)
         return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch * windows exceeds grid.z; split the batch");
     // 64x64 global blocks and 14x14 windows run on the tcgen05 kernels (attention_tc2.cu, attention_tc_win2.cu);
-    // CVLM_ATTN_LEGACY=1 forces the mma.sync kernel below (A/B comparisons, bisecting).
-    static const bool legacy = getenv("CVLM_ATTN_LEGACY") != nullptr && getenv("CVLM_ATTN_LEGACY")[0] == '1';
+    // cvlm_set_option("attn_legacy", 1) (or CVLM_ATTN_LEGACY=1 at start-up) forces the mma.sync kernel below (A/B comparisons, bisecting).
+    const bool legacy = option(OPT_ATTN_LEGACY) != 0;
     if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80))
         return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream);
     if (!legacy && window == 14 && (head_dim == 64 || head_dim == 80))

@@ -464,13 +464,19 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
         CVLM_TRY(make_tensor_map_bf16(&tw, r));
     }
     auto kern = attn_global_tc2_kernel<HD, POLY, PLAIN>;
-    CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-    {   // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
-        cudaFuncAttributes fa;
-        CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
-        if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
-            return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+    static unsigned char ready[kMaxDevices] = {};         // per (instantiation, device)
+    {
+        int dev = 0;
+        CVLM_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= kMaxDevices || !__atomic_load_n(&ready[dev], __ATOMIC_ACQUIRE)) {
+            // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
+            cudaFuncAttributes fa;
+            CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
+            if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
+                return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+        }
     }
+    CVLM_TRY(ensure_dynamic_smem(kern, G2_SMEM, ready));
     dim3 grid((tokens + 255) / 256, heads, batch);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eG2;
     kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens);
@@ -496,7 +502,7 @@ static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const vo
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
                                 int head_dim, cudaStream_t stream) {
     if (batch > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch exceeds grid.z; split the batch");
-    static const int poly = getenv("CVLM_ATTN_POLY") ? atoi(getenv("CVLM_ATTN_POLY")) : 4;
+    const int poly = option(OPT_ATTN_POLY);               // cvlm_set_option("attn_poly", n); default 4
     if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream);
     if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: head_dim %d", head_dim);

@@ -425,20 +425,21 @@ static int launch_window_tc2(const void* qkv, void* out, const void* relh, const
     if ((reinterpret_cast<uintptr_t>(relh) & 15) || (reinterpret_cast<uintptr_t>(relw) & 15))
         return set_error(CVLM_ERR_ARG, "attention: rel-pos tables must be 16-byte aligned");
     auto kern = attn_window_tc2_kernel<HD>;
-    CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM));
-    {   // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
-        cudaFuncAttributes fa;
-        CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
-        if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
-            return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc_win2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
-    }
-    const int items = batch * nW * nW * heads;
-    int sms = 148;
+    static unsigned char ready[kMaxDevices] = {};         // per (instantiation, device)
     {
         int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        CVLM_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= kMaxDevices || !__atomic_load_n(&ready[dev], __ATOMIC_ACQUIRE)) {
+            // setmaxnreg: 4 control warps shrink to 64, 8 softmax warps grow to 216 out of what those released
+            cudaFuncAttributes fa;
+            CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
+            if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
+                return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc_win2: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+        }
     }
+    CVLM_TRY(ensure_dynamic_smem(kern, W2_SMEM, ready));
+    const int items = batch * nW * nW * heads;
+    const int sms = device_sm_count();
     const int grid = items < sms ? items : sms;
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eW2;
     kern<<<grid, W2_THREADS, W2_SMEM, stream>>>(tq, static_cast<const __nv_bfloat16*>(relh), static_cast<const __nv_bfloat16*>(relw),

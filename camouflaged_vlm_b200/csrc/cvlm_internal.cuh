@@ -26,6 +26,27 @@ int set_error(int code, const char* fmt, ...);
         if (_rc != CVLM_OK) return _rc; \
     } while (0)
 
+// ---- per-device facts and test/tuning options (encoder.cu).  The library keeps no per-process device state: the SM
+// count and the "opt-in shared memory size already set" flags are per DEVICE (function attributes belong to a device's
+// context), so one process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+int device_sm_count();                      // SMs of the CURRENT device (cached per device)
+// one-time cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per (call site, device); `flags` is the call site's own
+// static array of kMaxDevices zero-initialised bytes
+template <typename Kern>
+int ensure_dynamic_smem(Kern kern, int bytes, unsigned char* flags) {
+    int dev = 0;
+    CVLM_CUDA(cudaGetDevice(&dev));
+    const int di = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    if (__atomic_load_n(&flags[di], __ATOMIC_ACQUIRE) && dev < kMaxDevices) return CVLM_OK;
+    CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    __atomic_store_n(&flags[di], static_cast<unsigned char>(1), __ATOMIC_RELEASE);
+    return CVLM_OK;
+}
+// cvlm_set_option (include/cvlm.h): read on the launch path as one relaxed atomic load, never getenv
+enum Option { OPT_GEMM_MODE = 0, OPT_DEC_CLUSTER, OPT_ATTN_LEGACY, OPT_ATTN_POLY, OPT_WIN_MODE, OPT_COUNT };
+int option(Option o);
+
 // ---- GEMM (gemm_tcgen05.cu):  out = epilogue(A1 * B1^T [+ A2 * B2^T])
 struct GemmArgs {
     const void* a1 = nullptr;  long long lda1 = 0;   // bf16 [M, K1], row stride lda1 elements

@@ -949,24 +949,24 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
     int dev = 0, sms = 148;
     CVLM_CUDA(cudaGetDevice(&dev));
     CVLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    static bool attr_done[64] = {};
-    static int cluster_ok[64][9] = {};      // per cluster size: 0 unknown, 1 schedulable, -1 not
-    const int di = dev & 63;
-    if (!attr_done[di]) {
-        CVLM_CUDA(cudaFuncSetAttribute(dec_token_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        CVLM_CUDA(cudaFuncSetAttribute(dec_token_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done[di] = true;
-    }
-    // CTAs per image on the token side: as many as keep the whole batch in one wave (CVLM_DEC_CLUSTER overrides: tests)
+    // first calls may come from several host threads at once: the flags are acquire/release bytes and the probe results
+    // relaxed ints that every thread would compute to the same value (a lost race repeats idempotent work)
+    static unsigned char attr_layer[kMaxDevices] = {}, attr_final[kMaxDevices] = {};
+    static int cluster_ok[kMaxDevices][9] = {};      // per cluster size: 0 unknown, 1 schedulable, -1 not
+    if (dev < 0 || dev >= kMaxDevices) return set_error(CVLM_ERR_UNSUPPORTED, "decoder_forward: device index %d", dev);
+    const int di = dev;
+    CVLM_TRY(ensure_dynamic_smem(dec_token_layer_kernel, 220 * 1024, attr_layer));
+    CVLM_TRY(ensure_dynamic_smem(dec_token_final_kernel, 220 * 1024, attr_final));
+    // CTAs per image on the token side: as many as keep the whole batch in one wave (option "dec_cluster" overrides: tests)
     int csize = 8;
     while (csize > 1 && batch * csize > sms) csize >>= 1;
-    if (const char* e = getenv("CVLM_DEC_CLUSTER")) {
-        const int v = atoi(e);
+    {
+        const int v = option(OPT_DEC_CLUSTER);       // cvlm_set_option("dec_cluster", n): tests
         if (v == 1 || v == 2 || v == 4 || v == 8) csize = v;
     }
     // a cluster of `csize` CTAs with this much shared memory each must be schedulable: ask once per size, fall back
     for (; csize > 1; csize >>= 1) {
-        if (cluster_ok[di][csize] == 0) {
+        if (__atomic_load_n(&cluster_ok[di][csize], __ATOMIC_RELAXED) == 0) {
             cudaLaunchAttribute qa[1];
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = csize;
@@ -981,7 +981,7 @@ int decoder_forward(cvlm_decoder* dec, const float* emb, const float* image_pe, 
             int n = 0;
             const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, dec_token_layer_kernel, &qc);
             if (qe != cudaSuccess) cudaGetLastError();
-            cluster_ok[di][csize] = (qe == cudaSuccess && n > 0) ? 1 : -1;
+            __atomic_store_n(&cluster_ok[di][csize], (qe == cudaSuccess && n > 0) ? 1 : -1, __ATOMIC_RELAXED);
         }
         if (cluster_ok[di][csize] == 1) break;
     }

@@ -13,6 +13,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -35,6 +38,38 @@ struct TensorRef {
     const void* ptr;
     long long nbytes;
 };
+
+int device_sm_count() {
+    static int sms[kMaxDevices] = {};       // 0 = not asked yet; written once per device with the same value
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    int n = cacheable ? __atomic_load_n(&sms[dev], __ATOMIC_RELAXED) : 0;
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cacheable) __atomic_store_n(&sms[dev], n, __ATOMIC_RELAXED);
+    }
+    return n;
+}
+
+// Options (cvlm_set_option): test / tuning hooks.  Their initial values come from the environment ONCE, at the first
+// use, so that `CVLM_GEMM_MODE=pair python tools/op_bench.py` keeps working; the launch path only loads an int.
+static const char* const kOptionNames[OPT_COUNT] = {"gemm_mode", "dec_cluster", "attn_legacy", "attn_poly", "win_mode"};
+static int g_options[OPT_COUNT];
+static std::once_flag g_options_once;
+static void options_from_env() {
+    for (int& v : g_options) v = 0;
+    g_options[OPT_ATTN_POLY] = 4;
+    if (const char* e = getenv("CVLM_GEMM_MODE")) g_options[OPT_GEMM_MODE] = e[0] == '1' ? 1 : e[0] == 'p' ? 2 : 0;
+    if (const char* e = getenv("CVLM_DEC_CLUSTER")) g_options[OPT_DEC_CLUSTER] = atoi(e);
+    if (const char* e = getenv("CVLM_ATTN_LEGACY")) g_options[OPT_ATTN_LEGACY] = e[0] == '1';
+    if (const char* e = getenv("CVLM_ATTN_POLY")) g_options[OPT_ATTN_POLY] = atoi(e);
+    if (const char* e = getenv("CVLM_WIN_MODE")) g_options[OPT_WIN_MODE] = atoi(e);
+}
+int option(Option o) {
+    std::call_once(g_options_once, options_from_env);
+    return __atomic_load_n(&g_options[o], __ATOMIC_RELAXED);
+}
 
 }  // namespace cvlm
 
@@ -396,6 +431,27 @@ extern "C" {
 
 const char* cvlm_last_error(void) { return g_err; }
 int cvlm_abi_version(void) { return 1; }
+
+int cvlm_set_option(const char* name, int value) {
+    if (!name) return set_error(CVLM_ERR_ARG, "set_option: null name");
+    option(OPT_GEMM_MODE);                               // make sure the environment defaults are in place first
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, kOptionNames[i])) {
+            __atomic_store_n(&g_options[i], value, __ATOMIC_RELAXED);
+            return CVLM_OK;
+        }
+    return set_error(CVLM_ERR_ARG, "set_option: unknown option '%s'", name);
+}
+
+int cvlm_get_option(const char* name, int* value) {
+    if (!name || !value) return set_error(CVLM_ERR_ARG, "get_option: null argument");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, kOptionNames[i])) {
+            *value = option(static_cast<Option>(i));
+            return CVLM_OK;
+        }
+    return set_error(CVLM_ERR_ARG, "get_option: unknown option '%s'", name);
+}
 
 int cvlm_encoder_create(const cvlm_encoder_config* cfg, cvlm_encoder** out) {
     if (!cfg || !out) return set_error(CVLM_ERR_ARG, "create: null argument");

@@ -561,16 +561,7 @@ static int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, lo
     return CVLM_OK;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return device_sm_count(); }     // per device (cvlm_internal.cuh)
 
 template <bool PAIR, int FEAT>
 static int launch_kernel(int total_tiles, cudaStream_t stream, const CUtensorMap& tA1, const CUtensorMap& tB1,
@@ -578,11 +569,8 @@ static int launch_kernel(int total_tiles, cudaStream_t stream, const CUtensorMap
                          int tiles_n, const GemmEpi& ep) {
     auto kern = gemm_bf16_tcgen05_kernel<PAIR, FEAT>;
     constexpr int smem = PAIR ? GEMM_SMEM_PAIR : GEMM_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CVLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static unsigned char attr_set[kMaxDevices] = {};      // per (instantiation, device): attributes belong to a context
+    CVLM_TRY(ensure_dynamic_smem(kern, smem, attr_set));
     if (PAIR) {   // clusters of two CTAs (one TPC): cta_group::2
         const int clusters = total_tiles < num_sms() / 2 ? total_tiles : num_sms() / 2;
         cudaLaunchConfig_t cfg = {};
@@ -652,11 +640,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (nbatch > 1 && (a.copy_bf16 || a.stat_out || a.ln_rows || a.res_row_mod > 0))
         return set_error(CVLM_ERR_ARG, "gemm: batched mode supports bias / GELU / residual / abs epilogues only");
     if (a.act_abs && a.out_bf16) return set_error(CVLM_ERR_ARG, "gemm: abs needs the fp32 output path");
-    // 256 x 256 cluster tiles whenever they fill the machine; CVLM_GEMM_MODE=1cta / pair forces one kernel
-    // (read per call: the parity tests flip it to cover both kernels on every shape).
-    const char* mode = getenv("CVLM_GEMM_MODE");
+    // 256 x 256 cluster tiles whenever they fill the machine; cvlm_set_option("gemm_mode", 1 | 2) forces one kernel
+    // (the parity tests flip it to cover both kernels on every shape)
+    const int mode = option(OPT_GEMM_MODE);
     const int pair_tiles = nbatch * ((a.m + 2 * BM - 1) / (2 * BM)) * ((a.n + BN - 1) / BN);
-    const bool pair = mode && mode[0] == 'p' ? true : mode && mode[0] == '1' ? false : pair_tiles >= num_sms() / 2;
+    const bool pair = mode == 2 ? true : mode == 1 ? false : pair_tiles >= num_sms() / 2;
     // narrow outputs (n <= 192) run the run-time-epilogue kernel with the MMA, the B box and the epilogue trimmed to
     // n_run columns.  The B box matters most: with a 256-row box over a 64-row weight matrix every k-block took 1.1 us
     // (0.5 us with the 128-row boxes of a CTA pair) however little the MMA had to do -- the time followed the number of
@@ -665,7 +653,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     int n_run = (a.n > 192 || a.stat_out) ? BN : (a.n + 63) / 64 * 64;
     // few tiles (small m: the batch-1 latency path of the CLIP tower and the decoder): a narrower N tile, run by the same
     // run-time kernel, puts more SMs to work (m = 579, n = 1024: 20 tiles of 256 columns -> 80 of 64)
-    if (n_run == BN && !pair && !a.stat_out && !a.ln_rows && nbatch == 1 && !(mode && mode[0] == '1')) {
+    if (n_run == BN && !pair && !a.stat_out && !a.ln_rows && nbatch == 1 && mode != 1) {
         const long long tm = (a.m + BM - 1) / BM;
         if (tm * ((a.n + BN - 1) / BN) * 2 <= num_sms()) {
             n_run = 128;

@@ -48,3 +48,47 @@ def encode_sharded(encode: Callable[[torch.Tensor], torch.Tensor], images: torch
     s, e = shard_range(images.shape[0], rank, world)
     local = encode(images[s:e])
     return gather_embeddings(local, images.shape[0])
+
+
+class ChunkGatherer:
+    """Pipelined embedding all-gather ("overlap with next micro-batch on a side stream").
+
+    A rank produces its ``per_rank`` embeddings chunk by chunk; ``submit(s, e, chunk)`` is called right after the
+    encoder of images [s, e) has been enqueued and starts the all-gather of that chunk on a side stream, so the
+    transfer runs underneath the encoder of the next chunk instead of after the whole batch.  Every rank ends up with
+    ``out`` = [world * per_rank, C, g, g] in rank-major order (rank r's image i at r * per_rank + i), the layout one
+    ``all_gather_into_tensor`` of the whole shard would give.  ``dtype=torch.bfloat16`` halves the bytes on the wire
+    (the embedding is rounded to bf16: ~1.1e-3 rel-L2 on top of the encoder's own error); ``finish()`` makes the
+    current stream wait for every gather and returns ``out``.  On CPU tensors (gloo, tests) everything is synchronous."""
+
+    def __init__(self, per_rank: int, tail, device, dtype=torch.float32):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.per_rank, self.dtype = per_rank, dtype
+        self.out = torch.empty((self.world * per_rank,) + tuple(tail), device=device, dtype=dtype)
+        self._by_rank = self.out.view((self.world, per_rank) + tuple(tail))
+        self.stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+        self.bytes_received = 0
+
+    def submit(self, s: int, e: int, chunk: torch.Tensor) -> None:
+        if chunk.shape[0] != e - s or not (0 <= s < e <= self.per_rank):
+            raise ValueError(f"chunk of {chunk.shape[0]} images does not cover [{s}, {e}) of {self.per_rank}")
+        if self.world == 1:
+            self._by_rank[0, s:e].copy_(chunk)
+            return
+        views = [self._by_rank[r, s:e] for r in range(self.world)]         # contiguous slices of `out`
+        self.bytes_received += (self.world - 1) * views[0].numel() * views[0].element_size()
+        if self.stream is None:
+            dist.all_gather(views, chunk.to(self.dtype).contiguous())
+            return
+        produced = torch.cuda.Event()
+        produced.record(torch.cuda.current_stream(chunk.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(produced)
+            src = chunk.to(self.dtype).contiguous()
+            dist.all_gather(views, src)
+        chunk.record_stream(self.stream)
+
+    def finish(self) -> torch.Tensor:
+        if self.stream is not None:
+            torch.cuda.current_stream(self.out.device).wait_stream(self.stream)
+        return self.out

@@ -285,7 +285,7 @@ class ImageEncoderViT(nn.Module):
         self._ensure_ready(x.device)
         lib = _lib.load()
         B = x.shape[0]
-        stream = _lib.stream_ptr()
+        stream = _lib.stream_ptr(x.device)          # torch's current stream on the TENSORS' device
         launches = 0
         for s in range(0, B, self.max_chunk):
             e = min(B, s + self.max_chunk)
@@ -296,21 +296,24 @@ class ImageEncoderViT(nn.Module):
                 arr = (C.c_void_p * len(interms))(*[t[s:e].data_ptr() for t in interms])
                 iptr = C.cast(arr, C.POINTER(C.c_void_p))
             # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu)
-            _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s, out[s:e].data_ptr(), iptr,
-                                                ws.data_ptr(), ws.numel(), stream), "cvlm_encoder_forward")
+            with torch.cuda.device(x.device):       # the C ABI launches on the CUDA current device
+                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s, out[s:e].data_ptr(), iptr,
+                                                    ws.data_ptr(), ws.numel(), stream), "cvlm_encoder_forward")
             launches += lib.cvlm_encoder_last_launch_count(self._handle)
         self.last_launch_count = launches
 
     @torch.no_grad()
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunk: int = 8,
-                     interm: bool = False, return_device: bool = False):
+                     interm: bool = False, return_device: bool = False, on_chunk=None):
         """Embeddings for a batch that lives in HOST memory (``x_host`` fp32 [B,3,S,S], ideally pinned): the batch is
         cut into chunks of ``chunk`` images; the host->device copy of chunk i+1 and the device->host copy of the
         embeddings of chunk i-1 run on a copy stream underneath the encoder of chunk i (two device staging buffers).
         Returns ``out_host`` ([B,out,g,g] fp32, pinned if allocated here), valid once the current stream has been
         synchronised.  ``return_device=True`` appends the device copy of the embeddings (e.g. to all-gather them
         across ranks, ``dist.gather_embeddings``); ``interm=True`` appends the list of per-global-block embeddings,
-        which stay on the device (NCHW views, like ``forward``)."""
+        which stay on the device (NCHW views, like ``forward``).  ``on_chunk(s, e, emb[s:e])`` is called on the main
+        stream right after the encoder of images [s, e) has been enqueued (e.g. ``dist.ChunkGatherer.submit``: the
+        all-gather of that chunk then runs under the next chunk's encoder)."""
         cfg = self._cfg
         if x_host.is_cuda:
             raise ValueError("forward_host takes a host tensor; call the module directly for device tensors")
@@ -349,6 +352,8 @@ class ImageEncoderViT(nn.Module):
             main.wait_event(ready[i % 2])
             self._run(stage[i % 2][:e - s], emb[s:e], [t[s:e] for t in interms])
             free[i % 2].record(main)
+            if on_chunk is not None:
+                on_chunk(s, e, emb[s:e])
             with torch.cuda.stream(cs):             # this chunk's embeddings go out under the next chunk's encoder
                 cs.wait_event(free[i % 2])
                 out_host[s:e].copy_(emb[s:e], non_blocking=True)
@@ -370,9 +375,10 @@ class ImageEncoderViT(nn.Module):
         B = x.shape[0]
         ws = self._get_workspace(B, x.device)
         xo = torch.empty(B * cfg.tokens, cfg.embed_dim, device=x.device, dtype=torch.float32)
-        _lib.check(lib.cvlm_encoder_forward_partial(self._handle, x.data_ptr(), None, B, stop_after_block,
-                                                    xo.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
-                   "cvlm_encoder_forward_partial")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cvlm_encoder_forward_partial(self._handle, x.data_ptr(), None, B, stop_after_block,
+                                                        xo.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        _lib.stream_ptr(x.device)), "cvlm_encoder_forward_partial")
         return xo
 
     # ------------------------------------------------------------------ fp32 check path (not the product)

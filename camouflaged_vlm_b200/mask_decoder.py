@@ -201,9 +201,12 @@ class MaskDecoder(nn.Module):
     def _depth(self) -> int:
         return len(self.transformer.layers)
 
+    def _weights_key(self, device):
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _handle_for(self, grid: int, cond_tokens: int, device) -> int:
         lib = _lib.load()
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = self._weights_key(device)
         if self._packed is None or self._packed_key != key:
             self._packed = pack_decoder_weights(dict(self.state_dict()), self._depth(), device)
             self._packed_key = key
@@ -232,8 +235,12 @@ class MaskDecoder(nn.Module):
         """predict_masks (mask_decoder_edge.py:140-190) for a batch: masks [B,4,4g,4g], edge [B,1,4g,4g], iou [B,4]."""
         if not image_embeddings.is_cuda:
             raise RuntimeError("MaskDecoder (B200) needs CUDA tensors: there is no CPU path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("MaskDecoder (B200) is inference only; call it under torch.no_grad() or freeze its parameters")
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (
+                image_embeddings, sparse_prompt_embeddings, dense_prompt_embeddings)):
+            # parameters with requires_grad=True (the default of a freshly built module) do not block inference;
+            # a differentiable INPUT does, because no gradient would reach it
+            raise RuntimeError("MaskDecoder (B200) is inference only: an input requires grad; detach it or call under "
+                               "torch.no_grad()")
         dev = image_embeddings.device
         B, Cc, g, g2 = image_embeddings.shape
         if Cc != self.transformer_dim or g != g2:
@@ -263,14 +270,16 @@ class MaskDecoder(nn.Module):
             e = min(B, s + self.max_chunk)
             need = _lib.check(lib.cvlm_decoder_workspace_bytes(h, e - s), "cvlm_decoder_workspace_bytes")
             if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-                self._workspace = None
+                # a CUDA graph that captured the old buffer keeps its own reference (graphed.py): replacing is safe
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._workspace
             db = dense.shape[0]
             dptr = dense.data_ptr() if db == 1 else dense[s:e].data_ptr()
-            _lib.check(lib.cvlm_decoder_forward(h, emb[s:e].data_ptr(), pe.data_ptr(), sparse[s:e].data_ptr(), dptr,
-                                                1 if db == 1 else e - s, e - s, masks[s:e].data_ptr(), edge[s:e].data_ptr(),
-                                                iou[s:e].data_ptr(), hs[s:e].data_ptr(), self._workspace.data_ptr(),
-                                                self._workspace.numel(), _lib.stream_ptr()), "cvlm_decoder_forward")
+            with torch.cuda.device(dev):        # the C ABI launches on the CUDA current device
+                _lib.check(lib.cvlm_decoder_forward(h, emb[s:e].data_ptr(), pe.data_ptr(), sparse[s:e].data_ptr(), dptr,
+                                                    1 if db == 1 else e - s, e - s, masks[s:e].data_ptr(), edge[s:e].data_ptr(),
+                                                    iou[s:e].data_ptr(), hs[s:e].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                    _lib.stream_ptr(dev)), "cvlm_decoder_forward")
             launches += lib.cvlm_decoder_last_launches(h)
         self.last_launch_count = launches
         self.last_hs = hs
@@ -308,8 +317,9 @@ def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     x = x.float().contiguous()
     n, c, h, w = x.shape
     out = torch.empty(n, c, size[0], size[1], device=x.device, dtype=torch.float32)
-    _lib.check(_lib.load().cvlm_op_bilinear_resize(x.data_ptr(), out.data_ptr(), n * c, h, w, size[0], size[1],
-                                                   _lib.stream_ptr()), "cvlm_op_bilinear_resize")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().cvlm_op_bilinear_resize(x.data_ptr(), out.data_ptr(), n * c, h, w, size[0], size[1],
+                                                       _lib.stream_ptr(x.device)), "cvlm_op_bilinear_resize")
     return out
 
 

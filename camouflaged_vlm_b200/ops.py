@@ -1,6 +1,7 @@
 """Op-level Python wrappers over the C ABI (include/cvlm.h ``cvlm_op_*``): torch tensors in, torch
 tensors out, launches on the current CUDA stream.  Used by the parity tests and for profiling single
 kernels; the encoder itself goes through ``cvlm_encoder_forward``.  No fallbacks: CUDA tensors only."""
+import functools
 from typing import Optional
 
 import torch
@@ -18,6 +19,22 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _on_tensor_device(fn):
+    """Run the wrapped op with its first tensor argument's device current: the C ABI launches on the CUDA current
+    device and ``_lib.stream_ptr()`` then names torch's current stream of THAT device, so an op on cuda:1 tensors works
+    whatever the caller's current device is.  All tensor arguments must live on one device."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        ts = [a for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor)]
+        _need_cuda(*ts)
+        if any(t.device != ts[0].device for t in ts):
+            raise RuntimeError(f"{fn.__name__}: tensors live on different devices: {sorted({str(t.device) for t in ts})}")
+        with torch.cuda.device(ts[0].device):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+@_on_tensor_device
 def gemm_bf16(a1: torch.Tensor, b1: torch.Tensor, a2: Optional[torch.Tensor] = None,
               b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, res_row_mod: int = 0, out_dtype=torch.float32,
@@ -62,6 +79,7 @@ def gemm_bf16(a1: torch.Tensor, b1: torch.Tensor, a2: Optional[torch.Tensor] = N
     return out
 
 
+@_on_tensor_device
 def ln_finalize(stat: torch.Tensor, width: int, eps: float) -> torch.Tensor:
     """[rows, groups, 2] partial (sum, sum of squares) -> [rows, 2] = (rstd, -mean * rstd)."""
     _need_cuda(stat)
@@ -72,6 +90,7 @@ def ln_finalize(stat: torch.Tensor, width: int, eps: float) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, batch: int, grid: int,
               window: int, heads: int, head_dim: int) -> torch.Tensor:
     _need_cuda(qkv, rel_pos_h, rel_pos_w)
@@ -83,6 +102,7 @@ def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tenso
     return out
 
 
+@_on_tensor_device
 def attention_plain(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
     """softmax(q k^T / sqrt(head_dim)) v per image, no relative-position terms; qkv bf16 [batch * tokens, 3 * heads * hd]."""
     _need_cuda(qkv)
@@ -93,6 +113,7 @@ def attention_plain(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head
     return out
 
 
+@_on_tensor_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype=torch.bfloat16):
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -104,6 +125,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+@_on_tensor_device
 def layernorm2d_nchw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, batch: int, tokens: int, eps: float):
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -115,6 +137,7 @@ def layernorm2d_nchw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, b
     return out
 
 
+@_on_tensor_device
 def im2col_patch16(img: torch.Tensor) -> torch.Tensor:
     _need_cuda(img)
     assert img.dtype == torch.float32 and img.is_contiguous()
@@ -126,6 +149,7 @@ def im2col_patch16(img: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def im2col_3x3(x: torch.Tensor, batch: int, grid: int) -> torch.Tensor:
     _need_cuda(x)
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
@@ -136,6 +160,7 @@ def im2col_3x3(x: torch.Tensor, batch: int, grid: int) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     out = torch.empty_like(x, dtype=torch.bfloat16)
@@ -144,6 +169,7 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def high_pass(images: torch.Tensor, pcat: torch.Tensor, npr: torch.Tensor, pi: torch.Tensor) -> torch.Tensor:
     """PromptGenerator.fft as two GEMMs with the low-pass projector (packing.high_pass_matrices)."""
     _need_cuda(images, pcat, npr, pi)
@@ -162,6 +188,7 @@ def high_pass(images: torch.Tensor, pcat: torch.Tensor, npr: torch.Tensor, pi: t
     return out
 
 
+@_on_tensor_device
 def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> torch.Tensor:
     _need_cuda(x0, hand, w_t, cst)
     out = torch.empty(batch * tokens, rank_pad, device=x0.device, dtype=torch.bfloat16)

@@ -36,8 +36,9 @@ def preprocess_u8(images: Union[torch.Tensor, Sequence[torch.Tensor]], size: int
                                     "cvlm_op_preprocess_u8_scratch_bytes"))
     # one scratch per image: the launches of consecutive images are independent and may overlap their tails
     scratch = torch.empty(len(images), (need + 255) // 256 * 256, dtype=torch.uint8, device=dev)
-    stream = _lib.stream_ptr()
-    for i, im in enumerate(images):
-        _lib.check(lib.cvlm_op_preprocess_u8(im.data_ptr(), im.shape[0], im.shape[1], out[i].data_ptr(), size, m, s,
-                                             scratch[i].data_ptr(), scratch.shape[1], stream), "cvlm_op_preprocess_u8")
+    stream = _lib.stream_ptr(dev)
+    with torch.cuda.device(dev):                # the C ABI launches on the CUDA current device
+        for i, im in enumerate(images):
+            _lib.check(lib.cvlm_op_preprocess_u8(im.data_ptr(), im.shape[0], im.shape[1], out[i].data_ptr(), size, m, s,
+                                                 scratch[i].data_ptr(), scratch.shape[1], stream), "cvlm_op_preprocess_u8")
     return out

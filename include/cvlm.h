@@ -39,6 +39,17 @@ typedef void* cvlm_stream_t; /* cudaStream_t */
 const char* cvlm_last_error(void);
 int cvlm_abi_version(void);
 
+/* Test / tuning switches, process-wide, read by the launchers as one integer load (no environment lookups on the
+ * launch path; the CVLM_* environment variables of the same meaning only provide the initial values):
+ *   "gemm_mode"    0 automatic, 1 one CTA per 128x256 tile, 2 CTA pairs (cta_group::2) per 256x256 tile
+ *   "dec_cluster"  0 automatic, 1/2/4/8 CTAs per image on the mask decoder's token side
+ *   "attn_legacy"  1 forces the mma.sync attention kernel (A/B runs)
+ *   "attn_poly"    how many of every 16 exponential pairs of the global attention run on the FMA pipe (0,2,4,6,8)
+ *   "win_mode"     window-attention kernel generation (0 = default)
+ * No reference analogue (the reference has no native layer on this path). */
+int cvlm_set_option(const char* name, int value);
+int cvlm_get_option(const char* name, int* value);
+
 /* ------------------------------------------------------------------------------------------------
  * Encoder handle.  Mirrors ImageEncoderViT.__init__ (image_encoder.py:26-44) after the Python side
  * has resolved norm_layer / act_layer to LayerNorm(eps) / GELU.

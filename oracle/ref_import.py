@@ -17,10 +17,37 @@ import types
 
 REF_ROOT = os.environ.get("CVLM_REFERENCE_ROOT", "/root/reference")
 SAM_DIR = os.path.join(REF_ROOT, "models", "mmseg", "models", "sam")
+# the two encoder files staged by oracle/stage_ref.py (git-ignored copy that travels to the GPU box, where
+# /root/reference does not exist); only the encoder is staged -- decoder / CLIP goldens are made in the container
+STAGED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "refsam")
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(SAM_DIR, "image_encoder.py"))
+
+
+def staged_encoder_available() -> bool:
+    return all(os.path.isfile(os.path.join(STAGED_DIR, f)) for f in ("image_encoder.py", "common.py"))
+
+
+def load_staged_encoder_module():
+    """The reference's image_encoder module from oracle/_ref/refsam (unmodified files, see oracle/stage_ref.py)."""
+    if not staged_encoder_available():
+        raise FileNotFoundError(f"no staged reference under {STAGED_DIR}: run oracle/stage_ref.py in the container")
+    if "refsam_staged" not in sys.modules:
+        pkg = types.ModuleType("refsam_staged")
+        pkg.__path__ = [STAGED_DIR]
+        sys.modules["refsam_staged"] = pkg
+    mods = []
+    for name in ("common", "image_encoder"):
+        full = f"refsam_staged.{name}"
+        if full not in sys.modules:
+            spec = importlib.util.spec_from_file_location(full, os.path.join(STAGED_DIR, f"{name}.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            spec.loader.exec_module(mod)
+        mods.append(sys.modules[full])
+    return mods[1]
 
 
 def _load(name: str):
@@ -53,13 +80,14 @@ def load_reference_decoder_modules():
     return _load("mask_decoder_edge"), _load("transformer_maskdecoder_edge")
 
 
-def build_reference_encoder(cfg):
-    """Instantiate the reference ImageEncoderViT the way models/sam_maskdecoder_edge.py:119-135 does."""
+def build_reference_encoder(cfg, staged: bool = False):
+    """Instantiate the reference ImageEncoderViT the way models/sam_maskdecoder_edge.py:119-135 does.
+    ``staged=True`` takes the class from oracle/_ref/refsam (the GPU box) instead of /root/reference."""
     from functools import partial
 
     import torch
 
-    enc, _ = load_reference_modules()
+    enc = load_staged_encoder_module() if staged else load_reference_modules()[0]
     return enc.ImageEncoderViT(
         img_size=cfg.img_size,
         patch_size=cfg.patch_size,

@@ -65,3 +65,38 @@ def test_encode_sharded_world2_gloo(total):
     assert ret["shape"][0] == total
     assert ret["err"] < 1e-5
     assert ret["same_on_all_ranks"]
+
+
+def _gather_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from camouflaged_vlm_b200.dist import ChunkGatherer
+    per_rank, tail = 5, (3, 2, 2)
+    full = torch.arange(world * per_rank * 12, dtype=torch.float32).reshape(world * per_rank, *tail) / 7.0
+    mine = full[rank * per_rank:(rank + 1) * per_rank]
+    ok = True
+    for dtype in (torch.float32, torch.bfloat16):
+        g = ChunkGatherer(per_rank, tail, "cpu", dtype)
+        for s in range(0, per_rank, 2):                      # ragged last chunk (2, 2, 1)
+            e = min(per_rank, s + 2)
+            g.submit(s, e, mine[s:e])
+        out = g.finish()
+        ok = ok and tuple(out.shape) == tuple(full.shape) and torch.equal(out, full.to(dtype))
+        ok = ok and g.bytes_received == (world - 1) * per_rank * 12 * out.element_size()
+    try:
+        ChunkGatherer(per_rank, tail, "cpu").submit(4, 6, mine[:2])
+        ok = False
+    except ValueError:
+        pass
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_chunk_gatherer_world2_gloo():
+    """Pipelined per-chunk all-gather (bench.py N>1 path): rank-major layout, ragged chunks, bf16 payload."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))

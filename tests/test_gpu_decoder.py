@@ -152,10 +152,12 @@ def test_decoder_rejects_bad_shapes():
 
 
 @pytest.mark.parametrize("csize", [1, 2, 4, 8])
-def test_decoder_token_cluster_sizes(csize, monkeypatch):
+def test_decoder_token_cluster_sizes(csize, request):
     # the token side runs one CTA cluster per image; every cluster size must give the same answer (up to the fp32
     # summation order of the K split) and match the oracle
-    monkeypatch.setenv("CVLM_DEC_CLUSTER", str(csize))
+    from camouflaged_vlm_b200 import _lib
+    _lib.set_option("dec_cluster", csize)
+    request.addfinalizer(lambda: _lib.set_option("dec_cluster", 0))
     dec, sd = build(1)
     gen = torch.Generator().manual_seed(21)
     emb = torch.randn(2, 256, 16, 16, generator=gen)
@@ -235,3 +237,34 @@ def test_graphed_decoder_and_tower_replay_bit_identical():
         with torch.no_grad():
             want = tfn(xi, al)
         assert torch.equal(tg(xi, al), want)
+
+
+def test_graph_survives_workspace_growth_and_detects_weight_change():
+    """a captured graph has the module's workspace and packed weights baked in.  A later eager call with a
+    larger batch replaces the module's workspace -- the graph must keep working on its own (kept-alive) buffer -- and a
+    parameter update must make the replay raise instead of running on stale packed weights."""
+    from camouflaged_vlm_b200.graphed import GraphedCall
+    dec, sd = build(0)
+    gen = torch.Generator().manual_seed(41)
+    emb = torch.randn(1, 256, 16, 16, generator=gen).cuda()
+    sparse = torch.randn(1, 2, 256, generator=gen).cuda()
+    pe = mdo.dense_pe(sd, 16).cuda()
+    dense = sd["probe.no_mask_embed"].reshape(1, -1, 1, 1).expand(1, -1, 16, 16).contiguous().cuda()
+    fn = lambda e, s: dec(e, [], pe, s, dense, False)
+    g = GraphedCall(fn, emb, sparse)
+    assert g._owners and g._owners[0] is dec                       # found through the lambda's closure
+    with torch.no_grad():
+        want = [t.clone() for t in fn(emb, sparse)]
+        ws_before = dec._workspace.data_ptr()
+        big = torch.randn(6, 256, 16, 16, generator=gen).cuda()
+        dec(big, [], pe, torch.randn(6, 2, 256, generator=gen).cuda(), dense, False)      # needs a larger workspace
+        assert dec._workspace.data_ptr() != ws_before
+        junk = torch.full((dec._workspace.numel() // 4,), float("nan"), device="cuda")     # churn the allocator
+        del junk
+    got = g(emb, sparse)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    with torch.no_grad():
+        next(dec.parameters()).add_(1.0)
+    with pytest.raises(RuntimeError, match="parameters changed"):
+        g(emb, sparse)

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from camouflaged_vlm_b200 import check_path as cp   # noqa: E402
-from camouflaged_vlm_b200 import ops                # noqa: E402
+from camouflaged_vlm_b200 import _lib, ops          # noqa: E402
 
 DEV = "cuda"
 
@@ -72,10 +72,11 @@ GEMM_SHAPES = [
 
 
 @pytest.fixture(params=["1cta", "pair"])
-def gemm_mode(request, monkeypatch):
+def gemm_mode(request):
     """Run a GEMM test through both kernels: one CTA per 128x256 tile, and CTA pairs (cta_group::2) per 256x256."""
-    monkeypatch.setenv("CVLM_GEMM_MODE", request.param)
-    return request.param
+    _lib.set_option("gemm_mode", {"1cta": 1, "pair": 2}[request.param])
+    yield request.param
+    _lib.set_option("gemm_mode", 0)
 
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
@@ -280,10 +281,10 @@ def test_attention_plain(batch, tokens, heads, hd):
 
 @pytest.mark.parametrize("m,n,k", [(579, 1024, 1024), (579, 1024, 4096), (579, 3072, 1024), (1737, 1024, 1024), (130, 520, 200),
                                    (64, 4096, 1024), (1, 776, 64)])
-def test_gemm_few_tiles_narrow_n(m, n, k, monkeypatch):
+def test_gemm_few_tiles_narrow_n(m, n, k):
     """Small-M problems (the batch-1 latency path) are cut into 128- or 64-column tiles by the launcher so that more SMs
     work; every epilogue must give the same numbers as the 256-column kernels, bit for bit (same K order per element)."""
-    monkeypatch.delenv("CVLM_GEMM_MODE", raising=False)
+    _lib.set_option("gemm_mode", 0)
     a = _randn(m, k, seed=500 + m, dtype=torch.bfloat16)
     b = _randn(n, k, seed=600 + n, dtype=torch.bfloat16, scale=0.05)
     bias = _randn(n, seed=700 + k)
@@ -293,6 +294,9 @@ def test_gemm_few_tiles_narrow_n(m, n, k, monkeypatch):
     assert _rel(got, want + res) < 2e-5
     got16 = ops.gemm_bf16(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16)
     assert _rel(got16.float(), torch.nn.functional.gelu(want)) < 4e-3
-    monkeypatch.setenv("CVLM_GEMM_MODE", "1cta")          # the 256-column kernel on the same problem
-    assert torch.equal(ops.gemm_bf16(a, b, bias=bias, residual=res), got)
-    assert torch.equal(ops.gemm_bf16(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16), got16)
+    _lib.set_option("gemm_mode", 1)                       # the 256-column kernel on the same problem
+    try:
+        assert torch.equal(ops.gemm_bf16(a, b, bias=bias, residual=res), got)
+        assert torch.equal(ops.gemm_bf16(a, b, bias=bias, gelu=True, out_dtype=torch.bfloat16), got16)
+    finally:
+        _lib.set_option("gemm_mode", 0)

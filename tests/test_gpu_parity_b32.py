@@ -1,0 +1,123 @@
+"""Parity on the configuration the headline is quoted on (BASELINE.json configs[1]): ViT-H, 1024^2, batch 32 in ONE
+C-ABI call (M = 131 072 token rows), called like the cascade calls it (``interm=True``,
+models/sam_maskdecoder_edge.py:337).
+
+* every image of the batch-32 call is BIT-EQUAL to the batch-1 call on that image (no cross-image state, the same
+  summation order per output element whatever the tile schedule);
+* the first 16 images are compared with the UNMODIFIED reference's embeddings (tests/golden/encoder_vit_h_multi.npz,
+  oracle/make_golden_vit_h_multi.py), rel-L2 <= 1e-2 each;
+* north-star mask gate over 16 images x 3 decoder seeds: binary masks of the downstream MaskDecoder_Edge from OUR
+  embedding vs the reference cascade's, MINIMUM IoU >= 0.99, distribution printed;
+* weights seeds 1..3 (other random draws of every parameter), one image each.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from camouflaged_vlm_b200 import PRESETS, build_encoder                  # noqa: E402
+from camouflaged_vlm_b200.synth import seeded_images, seeded_state_dict  # noqa: E402
+from oracle import encoder_oracle as orc                                 # noqa: E402
+from oracle import mask_decoder_oracle as mdo                            # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "encoder_vit_h_multi.npz")
+BF16_TOL = 1e-2          # north_star: embedding rel-L2 <= 1e-2 in bf16
+IOU_GATE = 0.99          # north_star: downstream binary masks IoU >= 0.99
+BATCH = 32
+
+
+def _encoder(seed=0):
+    cfg = PRESETS["vit_h"]
+    m = build_encoder(cfg).eval()
+    m.load_state_dict(seeded_state_dict(cfg, seed), strict=True)
+    return m.cuda()
+
+
+@pytest.fixture(scope="module")
+def batch32():
+    """One batch-32 forward (one C-ABI call, interm=True) shared by the tests below."""
+    cfg = PRESETS["vit_h"]
+    m = _encoder(0)
+    assert m.max_chunk >= BATCH
+    x = seeded_images(cfg, BATCH, 0).cuda()
+    with torch.no_grad():
+        out, interm = m(x, interm=True)
+    torch.cuda.synchronize()
+    return m, x, out, interm
+
+
+def test_batch32_one_call_equals_batch1_bit_for_bit(batch32):
+    m, x, out, interm = batch32
+    assert tuple(out.shape) == (BATCH, 256, 64, 64)
+    worst = 0.0
+    for k in range(BATCH):
+        with torch.no_grad():
+            o1, i1 = m(x[k:k + 1], interm=True)
+        if not torch.equal(o1[0], out[k]):
+            worst = max(worst, float((o1[0] - out[k]).abs().max()))
+        if k % 8 == 0:           # the four [1280,64,64] intermediate embeddings of a few images as well
+            for a, b in zip(i1, interm):
+                assert torch.equal(a[0], b[k]), f"interm embedding of image {k} depends on the batch size"
+    assert worst == 0.0, f"batch-32 result differs from batch-1 (max abs diff {worst:.3e})"
+    with torch.no_grad():
+        again = m(x)             # interm=False schedule (prompt fold at the global blocks too), run to run
+        again2 = m(x)
+    assert torch.equal(again, again2)
+    assert orc.rel_l2(again, out) < BF16_TOL
+
+
+def test_batch32_matches_reference_embeddings(batch32):
+    _, _, out, _ = batch32
+    g = np.load(GOLDEN)
+    s = int(g["stride"])
+    ref = torch.from_numpy(g["out_sub"])
+    n = ref.shape[0]
+    assert n >= 4
+    errs = [orc.rel_l2(out[i, :, ::s, ::s].cpu(), ref[i]) for i in range(n)]
+    norms = [abs(float(out[i].double().norm()) / float(g["out_norm"][i]) - 1.0) for i in range(n)]
+    print(f"embedding rel-L2 vs the reference, {n} images of the batch-32 call: min {min(errs):.3e} "
+          f"median {sorted(errs)[n // 2]:.3e} max {max(errs):.3e}; |norm ratio - 1| max {max(norms):.2e}")
+    assert max(errs) < BF16_TOL
+    assert max(norms) < 5e-3
+
+
+def test_mask_iou_16_images_3_decoder_seeds(batch32):
+    _, _, out, _ = batch32
+    g = np.load(GOLDEN)
+    logits = g["logits"]                      # [seeds, images, 256, 256] fp16: reference encoder -> reference decoder
+    n_seed, n_img = logits.shape[:2]
+    assert n_seed >= 3 and n_img >= 16
+    emb = out[:n_img].cpu()
+    scores = np.zeros((n_seed, n_img))
+    rel = np.zeros((n_seed, n_img))
+    for s in range(n_seed):
+        dsd = mdo.seeded_decoder_state(s)
+        for i in range(n_img):
+            got = mdo.decode_mask_logits(dsd, emb[i:i + 1])
+            want = torch.from_numpy(logits[s, i].astype(np.float32))[None, None]
+            scores[s, i] = mdo.iou(mdo.binary_mask(got, 1024), mdo.binary_mask(want, 1024))
+            rel[s, i] = orc.rel_l2(got, want)
+    flat = np.sort(scores.ravel())
+    print(f"downstream mask IoU over {n_img} images x {n_seed} decoder seeds: min {flat[0]:.5f} p10 {flat[len(flat) // 10]:.5f} "
+          f"median {flat[len(flat) // 2]:.5f} max {flat[-1]:.5f}; logits rel-L2 max {rel.max():.3e}")
+    assert flat[0] >= IOU_GATE, f"worst (seed, image) = {np.unravel_index(scores.argmin(), scores.shape)}"
+
+
+def test_other_weight_seeds_match_reference():
+    cfg = PRESETS["vit_h"]
+    g = np.load(GOLDEN)
+    s = int(g["stride"])
+    ref = g["wseed_out_sub"]
+    assert ref.shape[0] >= 3
+    for k in range(1, ref.shape[0] + 1):
+        m = _encoder(k)
+        with torch.no_grad():
+            out = m(seeded_images(cfg, 1, k).cuda())
+        err = orc.rel_l2(out[0, :, ::s, ::s].cpu(), torch.from_numpy(ref[k - 1]))
+        print(f"weights seed {k}: embedding rel-L2 {err:.3e}")
+        assert err < BF16_TOL
+        del m
+        torch.cuda.empty_cache()

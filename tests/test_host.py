@@ -99,3 +99,34 @@ def test_packing_shapes_and_folds():
     assert p["blk.0.relh"].shape == (2 * 14 - 1, 80) and p["blk.2.relh"].shape == (2 * cfg.grid - 1, 80)
     for t in p.values():
         assert t.is_contiguous()
+
+
+def test_options_round_trip_without_gpu(lib):
+    """cvlm_set_option / cvlm_get_option: the launchers read these instead of the environment (no getenv per launch)."""
+    for name, value in (("gemm_mode", 2), ("dec_cluster", 4), ("attn_legacy", 1), ("attn_poly", 6), ("win_mode", 1)):
+        before = _lib.get_option(name)
+        _lib.set_option(name, value)
+        assert _lib.get_option(name) == value
+        _lib.set_option(name, before)
+    with pytest.raises(_lib.CvlmError):
+        _lib.set_option("no_such_option", 1)
+
+
+def test_staged_reference_is_the_reference_verbatim():
+    """oracle/stage_ref.py: oracle/_ref/refsam holds byte-identical copies of the reference's two encoder files and the
+    staged module computes what the in-place reference computes (container only)."""
+    import filecmp
+    from oracle import ref_import, stage_ref
+    if not ref_import.reference_available():
+        pytest.skip("needs /root/reference")
+    assert stage_ref.stage(verbose=False)
+    for f in stage_ref.FILES:
+        assert filecmp.cmp(os.path.join(stage_ref.SRC_DIR, f), os.path.join(stage_ref.DST_DIR, f), shallow=False)
+    cfg = PRESETS["tiny"]
+    sd = seeded_state_dict(cfg, 0)
+    a, b = ref_import.build_reference_encoder(cfg).eval(), ref_import.build_reference_encoder(cfg, staged=True).eval()
+    a.load_state_dict(sd, strict=True)
+    b.load_state_dict(sd, strict=True)
+    x = seeded_images(cfg, 1)
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))
