@@ -81,6 +81,24 @@ _SIGS = {
     "cvlm_encoder_last_launch_count": (C.c_longlong, [C.c_void_p]),
     "cvlm_encoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cvlm_encoder_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "cvlm_encoder_saved_bytes": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "cvlm_encoder_backward_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "cvlm_encoder_grad_floats": (C.c_longlong, [C.c_void_p]),
+    "cvlm_encoder_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "cvlm_encoder_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
+                                             C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_encoder_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_longlong,
+                                        C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_op_attention_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvlm_op_ln_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "cvlm_op_wgrad_tn_jp": (C.c_int, [C.c_int, C.c_int]),
+    "cvlm_op_wgrad_tn_splits": (C.c_int, [C.c_longlong]),
+    "cvlm_op_wgrad_tn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_longlong,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvlm_op_gemm_bf16_dgelu": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_op_gemm_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                     C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,

@@ -88,6 +88,10 @@ struct GemmArgs {
     // [0, m)), so no im2col matrix is ever written.  Output rows at border pixels are meaningless; the caller zeroes or
     // ignores them.  k1 must be 576.
     int conv_pitch = 0;
+    // Training (adapter-only backward).  bf16 path: `copy_bf16` also receives the PRE-activation value
+    // (what the backward of the GELU needs); `aux` (bf16 [m, ldaux]) makes the epilogue multiply by gelu'(aux): the
+    // backward of lin2 / shared_mlp into the GELU that precedes them.
+    const void* aux = nullptr;  long long ldaux = 0;
 };
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
@@ -103,6 +107,23 @@ int attention_plain_tc2_launch(const void* qkv, void* out, int batch, int tokens
 
 int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                                 int heads, int head_dim, cudaStream_t stream);
+
+// ---- backward pass for adapter-only training (attention_bwd.cu, backward.cu)
+int attention_backward_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
+                              const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
+                              int head_dim, cudaStream_t stream);
+int layernorm_train_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, void* xhat_bf16,
+                           float* rstd, long long rows, int cols, float eps, cudaStream_t stream);
+int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void* xsrc, const float* stat,
+                  const float* residual, float* dx, void* dxb, long long rows, int cols, float eps, cudaStream_t stream);
+int wgrad_splits(long long m);
+int wgrad_jp(int j, int ones);
+int wgrad_tn_launch(const void* A, long long lda, int I, const void* B, long long ldb, int J, int ones, long long M,
+                    float* partial, int accumulate, cudaStream_t stream);
+int wgrad_reduce_launch(const float* partial, int splits, long long n, float* out, cudaStream_t stream);
+int add_f32_launch(float* y, const float* x, long long n, cudaStream_t stream);
+int eg_wgrad_launch(const void* x0b, const void* dt, int batch, int tokens, int dim, int rank_pad, float* partial,
+                    cudaStream_t stream);
 
 // ---- row kernels (rowops.cu)
 int layernorm_launch(const float* x, const float* gamma, const float* beta, void* out, int out_bf16, long long rows,

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "cvlm_internal.cuh"
+#include "encoder_runtime.cuh"
 
 namespace cvlm {
 
@@ -33,11 +34,6 @@ int set_error(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
-
-struct TensorRef {
-    const void* ptr;
-    long long nbytes;
-};
 
 int device_sm_count() {
     static int sms[kMaxDevices] = {};       // 0 = not asked yet; written once per device with the same value
@@ -73,29 +69,7 @@ int option(Option o) {
 
 }  // namespace cvlm
 
-struct ProfSpan {
-    int kind;
-    cudaEvent_t start, stop;
-};
-
-struct cvlm_encoder {
-    cvlm_encoder_config cfg;
-    std::unordered_map<std::string, cvlm::TensorRef> tensors;
-    long long last_launches = 0;
-    bool profiling = false;
-    std::vector<ProfSpan> spans;        // spans of the profiled forwards since the last get_profile
-    std::vector<cudaEvent_t> event_pool;
-};
-
 namespace cvlm {
-
-enum ProfKind {
-    K_GEMM_QKV = 0, K_GEMM_PROJ, K_GEMM_LIN1, K_GEMM_LIN2, K_GEMM_OTHER, K_ATTN_WINDOW, K_ATTN_GLOBAL, K_LAYERNORM,
-    K_OTHER, K_COUNT
-};
-static_assert(K_COUNT == CVLM_PROF_KINDS, "cvlm.h CVLM_PROF_KINDS out of sync");
-
-static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
     long long off_x, off_a, off_big, off_hand, off_t, off_gall, total;
@@ -134,56 +108,40 @@ static Workspace plan_workspace(const cvlm_encoder_config& c, int batch) {
     return w;
 }
 
-struct Fwd {
-    cvlm_encoder* enc;
-    cudaStream_t stream;
-    long long launches = 0;
-    char namebuf[96];
+// Activations the training forward keeps for the backward pass (encoder_train.cu), carved out of one caller-provided
+// region.  Per image (ViT-H): 105 MB per block (block input bf16 + LayerNorm rows, qkv, attention output, the
+// normalised norm2 input, the pre-GELU hidden) + 45 MB of stem / adapter / neck state = 3.4 GB.
+Saved plan_saved(const cvlm_encoder_config& c, int batch) {
+    const long long g = c.img_size / c.patch_size, T = g * g, M = T * batch;
+    const long long D = c.embed_dim, OC = c.out_chans, RP = c.rank_pad;
+    const long long kp = static_cast<long long>(c.in_chans) * c.patch_size * c.patch_size;
+    Saved s;
+    long long off = 0;
+    auto take = [&](long long bytes) { const long long o = off; off = align_up(off + bytes, 1024); return o; };
+    s.off_x0b = take(M * D * 2);
+    s.off_php = take(M * kp * 2);
+    s.off_t = take(M * RP * 2);
+    s.off_gall = take(M * c.depth * RP * 2);
+    s.off_gpre = take(M * c.depth * RP * 2);
+    s.off_n1 = take(M * OC * 4);
+    s.off_n2 = take(M * OC * 4);
+    s.off_blocks = off;
+    off = 0;
+    s.b_xb = take(M * D * 2);
+    s.b_rows1 = take(M * 8);
+    s.b_qkv = take(M * 3 * D * 2);
+    s.b_o = take(M * D * 2);
+    s.b_xh2 = take(M * D * 2);
+    s.b_rstd2 = take(M * 4);
+    s.b_hpre = take(M * c.mlp_dim * 2);
+    s.block_stride = off;
+    s.total = s.off_blocks + s.block_stride * c.depth;
+    return s;
+}
 
-    int get(const char* name, long long expect_bytes, const void** out) {
-        auto it = enc->tensors.find(name);
-        if (it == enc->tensors.end()) return set_error(CVLM_ERR_MISSING, "tensor '%s' was not registered", name);
-        if (expect_bytes > 0 && it->second.nbytes != expect_bytes)
-            return set_error(CVLM_ERR_MISSING, "tensor '%s' has %lld bytes, expected %lld", name, it->second.nbytes,
-                             expect_bytes);
-        *out = it->second.ptr;
-        return CVLM_OK;
-    }
-    int getb(int blk, const char* suffix, long long expect_bytes, const void** out) {
-        snprintf(namebuf, sizeof(namebuf), "blk.%d.%s", blk, suffix);
-        return get(namebuf, expect_bytes, out);
-    }
-    cudaEvent_t event() {
-        if (!enc->event_pool.empty()) {
-            cudaEvent_t e = enc->event_pool.back();
-            enc->event_pool.pop_back();
-            return e;
-        }
-        cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        return e;
-    }
-    // every kernel launch of the forward goes through here: counts it and, when profiling is on,
-    // brackets it with CUDA events on the launching stream
-    template <typename F>
-    int run(int kind, F&& launch) {
-        ++launches;
-        if (!enc->profiling) return launch();
-        ProfSpan sp{kind, event(), event()};
-        cudaEventRecord(sp.start, stream);
-        const int rc = launch();
-        cudaEventRecord(sp.stop, stream);
-        enc->spans.push_back(sp);
-        return rc;
-    }
-    int gemm(int kind, const GemmArgs& a) {
-        return run(kind, [&] { return gemm_launch(a, stream); });
-    }
-};
-
-static int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
-                        float* const* interm, int stop_after_block, float* x_out, void* workspace,
-                        long long workspace_bytes, cudaStream_t stream) {
+int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
+                 float* const* interm, int stop_after_block, float* x_out, void* workspace,
+                 long long workspace_bytes, void* saved, long long saved_bytes, cudaStream_t stream) {
     if (!enc || !images || !workspace) return set_error(CVLM_ERR_ARG, "forward: null argument");
     if (batch <= 0) return set_error(CVLM_ERR_ARG, "forward: batch must be positive");
     const cvlm_encoder_config& c = enc->cfg;
@@ -204,18 +162,33 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
     __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_t);
     __nv_bfloat16* gall = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_gall);
     const long long ldg = static_cast<long long>(depth) * RP;
-    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(wsb + ws.off_xb);
     float* stat = reinterpret_cast<float*>(wsb + ws.off_stat);
-    float* lnrows = reinterpret_cast<float*>(wsb + ws.off_rows);
     const int sgroups = (D + CVLM_STAT_GROUP_COLS - 1) / CVLM_STAT_GROUP_COLS;
-    // norm1 is folded around the GEMMs (cvlm_internal.cuh, GemmArgs): the GEMM that writes a block's input (lin2 of the
-    // previous block, or the prompt add) also leaves bf16(x) in `xb` and partial row statistics, which ln_finalize
-    // reduces for the qkv GEMM
-    auto feeds_norm = [&](GemmArgs& ga) {
-        ga.copy_bf16 = xb; ga.ldc = D; ga.stat_out = stat; ga.stat_groups = sgroups;
+    // Training forward (saved != NULL): every tensor the backward pass needs goes to its own slot of `saved` instead
+    // of a re-used workspace buffer; the schedule and the arithmetic are the inference ones.
+    const bool train = saved != nullptr;
+    const Saved sv = plan_saved(c, batch);
+    char* svb = static_cast<char*>(saved);
+    if (train) {
+        if (saved_bytes < sv.total) return set_error(CVLM_ERR_WORKSPACE, "saved-activation region has %lld bytes, need %lld", saved_bytes, sv.total);
+        if (reinterpret_cast<uintptr_t>(saved) & 255) return set_error(CVLM_ERR_ARG, "saved-activation region must be 256-byte aligned");
+        if (stop_after_block >= 0 || x_out) return set_error(CVLM_ERR_ARG, "forward_partial has no training mode");
+        t = reinterpret_cast<__nv_bfloat16*>(svb + sv.off_t);
+        gall = reinterpret_cast<__nv_bfloat16*>(svb + sv.off_gall);
+    }
+    auto blk_ptr = [&](int blk, long long off) { return svb + sv.off_blocks + sv.block_stride * blk + off; };
+    // norm1 is folded around the GEMMs (cvlm_internal.cuh, GemmArgs): the GEMM that writes block `blk`'s input (lin2 of
+    // the previous block, or the prompt add) also leaves bf16(x) and partial row statistics, which ln_finalize reduces
+    // to (rstd, -mean * rstd) per row for that block's qkv GEMM
+    auto xb_of = [&](int blk) {
+        return reinterpret_cast<__nv_bfloat16*>(train ? blk_ptr(blk, sv.b_xb) : wsb + ws.off_xb);
     };
-    auto normed = [&](GemmArgs& ga, const void* colsum) {
-        ga.ln_rows = lnrows; ga.ln_colsum = static_cast<const float*>(colsum);
+    auto rows_of = [&](int blk) { return reinterpret_cast<float*>(train ? blk_ptr(blk, sv.b_rows1) : wsb + ws.off_rows); };
+    auto feeds_norm = [&](GemmArgs& ga, int blk) {
+        ga.copy_bf16 = xb_of(blk); ga.ldc = D; ga.stat_out = stat; ga.stat_groups = sgroups;
+    };
+    auto normed = [&](GemmArgs& ga, const void* colsum, int blk) {
+        ga.ln_rows = rows_of(blk); ga.ln_colsum = static_cast<const float*>(colsum);
     };
 
     Fwd f{enc, stream};
@@ -249,7 +222,7 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         highpass = hp;
     }
     __nv_bfloat16* patches = big;
-    __nv_bfloat16* patches_hp = big + M * kp;
+    __nv_bfloat16* patches_hp = train ? reinterpret_cast<__nv_bfloat16*>(svb + sv.off_php) : big + M * kp;
     CVLM_TRY(f.run(K_OTHER, [&] { return im2col_patch_launch(images, patches, batch, c.in_chans, c.img_size, c.patch_size, stream); }));
     CVLM_TRY(f.run(K_OTHER, [&] { return im2col_patch_launch(highpass, patches_hp, batch, c.in_chans, c.img_size, c.patch_size, stream); }));
     {   // PatchEmbed (:655-659) + pos_embed (:139-140): x = patches * Wp^T + bp + pos[row % T]
@@ -258,6 +231,13 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(patch_b);
         ga.residual = static_cast<const float*>(pos); ga.ldr = D; ga.res_row_mod = T;
         ga.out = x; ga.ldo = D;
+        CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
+    }
+    if (train) {   // the patch embedding WITHOUT pos_embed, bf16: input of embedding_generator, needed for its weight gradient
+        GemmArgs ga;
+        ga.a1 = patches; ga.lda1 = kp; ga.b1 = patch_w; ga.ldb1 = kp; ga.k1 = kp;
+        ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(patch_b);
+        ga.out = svb + sv.off_x0b; ga.ldo = D; ga.out_bf16 = 1;
         CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
     }
     {   // PatchEmbed2 of the high-passed image (:283-285): hand = patches_hp * Wh^T + bh   (fp32 [M, RP])
@@ -276,10 +256,13 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         ga.a1 = t; ga.lda1 = RP; ga.b1 = lw_w; ga.ldb1 = RP; ga.k1 = RP;
         ga.m = static_cast<int>(M); ga.n = static_cast<int>(ldg); ga.bias = static_cast<const float*>(lw_b);
         ga.out = gall; ga.ldo = ldg; ga.out_bf16 = 1; ga.act_gelu = 1;
+        if (train) {   // pre-activation values for the backward of the GELU
+            ga.copy_bf16 = svb + sv.off_gpre; ga.ldc = ldg;
+        }
         CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
     }
-    auto finalize_norm = [&]() -> int {
-        return f.run(K_LAYERNORM, [&] { return ln_finalize_launch(stat, sgroups, D, c.ln_eps, lnrows, M, stream); });
+    auto finalize_norm = [&](int blk) -> int {
+        return f.run(K_LAYERNORM, [&] { return ln_finalize_launch(stat, sgroups, D, c.ln_eps, rows_of(blk), M, stream); });
     };
     auto prompt_add = [&](int blk, const float* src, float* dst) -> int {
         // dst = src + gall_blk * Wshared^T + bshared    (shared_mlp :294, add :145); dst is the next norm1 input
@@ -287,9 +270,9 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         ga.a1 = gall + static_cast<long long>(blk) * RP; ga.lda1 = ldg; ga.b1 = sh_w; ga.ldb1 = RP; ga.k1 = RP;
         ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(sh_b);
         ga.residual = src; ga.ldr = D; ga.out = dst; ga.ldo = D;
-        feeds_norm(ga);
+        feeds_norm(ga, blk);
         CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
-        return finalize_norm();
+        return finalize_norm(blk);
     };
     CVLM_TRY(prompt_add(0, x, x));
 
@@ -324,20 +307,22 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         CVLM_TRY(f.getb(i, "lin2.b", 4LL * D, &l2b));
         if (i + 1 < depth) CVLM_TRY(f.getb(i, "lin2.bf", 4LL * D, &l2bf));
 
+        __nv_bfloat16* qkv_buf = train ? reinterpret_cast<__nv_bfloat16*>(blk_ptr(i, sv.b_qkv)) : big;
+        __nv_bfloat16* attn_out = train ? reinterpret_cast<__nv_bfloat16*>(blk_ptr(i, sv.b_o)) : a;
         {   // norm1 (:436) + qkv (:491) on the raw bf16 residual stream; bias = W beta1 + [b_q, 0, 0]
             GemmArgs ga;
-            ga.a1 = xb; ga.lda1 = D; ga.b1 = qkv_w; ga.ldb1 = D; ga.k1 = D;
+            ga.a1 = xb_of(i); ga.lda1 = D; ga.b1 = qkv_w; ga.ldb1 = D; ga.k1 = D;
             ga.m = static_cast<int>(M); ga.n = 3 * D; ga.bias = static_cast<const float*>(qkv_b);
-            ga.out = big; ga.ldo = 3 * D; ga.out_bf16 = 1;
-            normed(ga, qkv_c);
+            ga.out = qkv_buf; ga.ldo = 3 * D; ga.out_bf16 = 1;
+            normed(ga, qkv_c, i);
             CVLM_TRY(f.gemm(K_GEMM_QKV, ga));
         }
         CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
-            return attention_launch(big, a, relh, relw, batch, g, window, c.num_heads, hd, stream);
+            return attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream);
         }));
         {   // proj (:502) + shortcut (:443); bias = b_proj + W_proj * b_v
             GemmArgs ga;
-            ga.a1 = a; ga.lda1 = D; ga.b1 = proj_w; ga.ldb1 = D; ga.k1 = D;
+            ga.a1 = attn_out; ga.lda1 = D; ga.b1 = proj_w; ga.ldb1 = D; ga.k1 = D;
             ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(proj_b);
             ga.residual = xcur; ga.ldr = D; ga.out = xcur; ga.ldo = D;
             CVLM_TRY(f.gemm(K_GEMM_PROJ, ga));
@@ -345,6 +330,10 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
         // norm2 (:444) stays a kernel: proj (HBM-bound residual epilogue) and lin1 (GELU epilogue) are the two GEMMs
         // that cannot absorb the producer / consumer halves of the fold for free (measured: +5.2 ms and +6.6 ms per step)
         CVLM_TRY(f.run(K_LAYERNORM, [&] {
+            if (train)   // also keeps the normalised input (bf16) and 1/std per row for the backward of norm2
+                return layernorm_train_launch(xcur, static_cast<const float*>(ln2w), static_cast<const float*>(ln2b), a,
+                                              blk_ptr(i, sv.b_xh2), reinterpret_cast<float*>(blk_ptr(i, sv.b_rstd2)), M, D,
+                                              c.ln_eps, stream);
             return layernorm_launch(xcur, static_cast<const float*>(ln2w), static_cast<const float*>(ln2b), a, 1, M, D,
                                     c.ln_eps, stream);
         }));
@@ -353,6 +342,9 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
             ga.a1 = a; ga.lda1 = D; ga.b1 = l1w; ga.ldb1 = D; ga.k1 = D;
             ga.m = static_cast<int>(M); ga.n = c.mlp_dim; ga.bias = static_cast<const float*>(l1b);
             ga.out = big; ga.ldo = c.mlp_dim; ga.out_bf16 = 1; ga.act_gelu = 1;
+            if (train) {   // pre-GELU hidden for the backward pass
+                ga.copy_bf16 = blk_ptr(i, sv.b_hpre); ga.ldc = c.mlp_dim;
+            }
             CVLM_TRY(f.gemm(K_GEMM_LIN1, ga));
         }
         const bool want_interm = interm != nullptr && c.is_global[i];
@@ -368,9 +360,9 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
             }
             ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(fold ? l2bf : l2b);
             ga.residual = xcur; ga.ldr = D; ga.out = dst; ga.ldo = D;
-            if (fold) feeds_norm(ga);      // otherwise prompt_add below writes the next norm1 input
+            if (fold) feeds_norm(ga, i + 1);      // otherwise prompt_add below writes the next norm1 input
             CVLM_TRY(f.gemm(K_GEMM_LIN2, ga));
-            if (fold) CVLM_TRY(finalize_norm());
+            if (fold) CVLM_TRY(finalize_norm(i + 1));
         }
         if (want_interm) ++interm_idx;
         if (stop_here) return finish_partial(dst);
@@ -394,8 +386,8 @@ static int forward_impl(cvlm_encoder* enc, const float* images, const float* hig
     CVLM_TRY(f.run(K_OTHER, [&] { return cast_bf16_launch(xcur, a, M * D, stream); }));
     // n1 / n2 live in the (now dead) x region unless the final residual stream is x itself being read...
     // the cast above already consumed it, so the region is free either way.
-    float* n1 = x;
-    float* n2 = x + M * OC;
+    float* n1 = train ? reinterpret_cast<float*>(svb + sv.off_n1) : x;
+    float* n2 = train ? reinterpret_cast<float*>(svb + sv.off_n2) : x + M * OC;
     {   // 1x1 conv, no bias
         GemmArgs ga;
         ga.a1 = a; ga.lda1 = D; ga.b1 = c1w; ga.ldb1 = D; ga.k1 = D;
@@ -501,7 +493,7 @@ long long cvlm_encoder_workspace_bytes(const cvlm_encoder* enc, int batch) {
 
 int cvlm_encoder_forward(cvlm_encoder* enc, const float* images, const float* highpass, int batch, float* out,
                          float* const* interm, void* workspace, long long workspace_bytes, cvlm_stream_t stream) {
-    return forward_impl(enc, images, highpass, batch, out, interm, -1, nullptr, workspace, workspace_bytes,
+    return forward_impl(enc, images, highpass, batch, out, interm, -1, nullptr, workspace, workspace_bytes, nullptr, 0,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -510,7 +502,7 @@ int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const f
                                  cvlm_stream_t stream) {
     if (!x_out) return set_error(CVLM_ERR_ARG, "forward_partial: null x_out");
     return forward_impl(enc, images, highpass, batch, nullptr, nullptr, stop_after_block, x_out, workspace,
-                        workspace_bytes, static_cast<cudaStream_t>(stream));
+                        workspace_bytes, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 long long cvlm_encoder_last_launch_count(const cvlm_encoder* enc) { return enc ? enc->last_launches : 0; }

@@ -65,6 +65,8 @@ struct GemmEpi {
     int conv_pitch;               // > 0: implicit 3x3 convolution over a zero-bordered raster map (GemmArgs::conv_pitch)
     int n_run;                    // run-time-epilogue kernel: accumulator columns the MMA really computes (64, 128, 192 or
                                   // 256): a narrow output does not pay for a 256-wide tile on the tensor pipe
+    const __nv_bfloat16* aux;     // bf16 path, backward of a GELU layer: out = acc * gelu'(aux[row, col])
+    long long ldaux;
 };
 
 // Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
@@ -103,6 +105,23 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
     return f32x2_fma(ax2, p, f32x2_relu(x2));
 }
 
+// d/dx of the exact-erf GELU, same erf approximation as gelu_erf:  gelu'(x) = Phi(x) + x * phi(x)
+// (backward of MLPBlock / lightweight_mlp for adapter training)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float ax = fabsf(x);
+    const float zs = ax * 0.8493218002880191f;                 // |x| / sqrt(2) * sqrt(log2 e)
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, zs, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-zs * zs));             // exp(-x^2 / 2)
+    float p = fmaf(t, 0.5307027145f, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    const float half_erfc = p * t * e;                          // 0.5 * erfc(|x| / sqrt 2)
+    const float phi_cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+    return fmaf(x * 0.3989422804014327f, e, phi_cdf);
+}
+
 // PAIR = false: one CTA per 128 x 256 tile (small problems).
 // PAIR = true : a cluster of two CTAs (one TPC) per 256 x 256 tile, tcgen05.mma.cta_group::2.  Each CTA stages its own
 //   128 rows of A and HALF of the B tile (128 of the 256 weight rows), so the tensor core's shared-memory operand
@@ -118,6 +137,9 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
 //   F_STATIC    the epilogue type is a compile-time fact: F_BF16 (bf16 output), F_GELU, F_RES (fp32 residual) say which;
 //               without it those three are read from GemmEpi at run time (stem / adapter / neck GEMMs)
 constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64, F_QUICK = 128;
+//   F_DGELU     bf16 path: multiply by gelu'(aux) (backward of a GELU layer).  On the bf16 path F_PRODUCER means "also
+//               store the PRE-activation value as bf16 in copy_bf16" (what that backward needs from the forward).
+constexpr int F_DGELU = 256;
 // QuickGELU of CLIP (alpha_clip_rw/model.py:171-173): x * sigmoid(1.702 x); GemmArgs::act_gelu == 2
 __device__ __forceinline__ float quick_gelu(float x) {
     return x * __frcp_rn(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x));
@@ -435,6 +457,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
                             }
+                            if ((FEAT & F_PRODUCER) && ep.copy_bf16 != nullptr) {
+                                // training forward: keep the pre-activation value for the backward pass
+                                uint4 pre;
+                                float lo, hi;
+                                f32x2_unpack(y[0], lo, hi); pre.x = pack_bf16(lo, hi);
+                                f32x2_unpack(y[1], lo, hi); pre.y = pack_bf16(lo, hi);
+                                f32x2_unpack(y[2], lo, hi); pre.z = pack_bf16(lo, hi);
+                                f32x2_unpack(y[3], lo, hi); pre.w = pack_bf16(lo, hi);
+                                *reinterpret_cast<uint4*>(ep.copy_bf16 + (brow + row) * ep.ldc + col) = pre;
+                            }
                             if (act_gelu) {
                                 if (act_quick) {
 #pragma unroll
@@ -442,6 +474,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 } else {
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) y[e] = gelu_erf2(y[e]);
+                                }
+                            }
+                            if (((FEAT & F_DGELU) || !(FEAT & F_STATIC)) && ep.aux != nullptr) {
+                                const uint4 ax = *reinterpret_cast<const uint4*>(ep.aux + (brow + row) * ep.ldaux + col);
+                                const uint32_t aw[4] = {ax.x, ax.y, ax.z, ax.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float lo, hi;
+                                    f32x2_unpack(y[e], lo, hi);
+                                    lo *= gelu_erf_grad(__uint_as_float(aw[e] << 16));
+                                    hi *= gelu_erf_grad(__uint_as_float(aw[e] & 0xffff0000u));
+                                    y[e] = f32x2_pack(lo, hi);
                                 }
                             }
                             if (has_res) {
@@ -602,6 +646,9 @@ constexpr int V_LIN1 = F_STATIC | F_BF16 | F_GELU;              // lin1 + GELU
 constexpr int V_LIN2 = F_STATIC | F_RES | F_PRODUCER;           // lin2 + shortcut, feeds the next norm1
 constexpr int V_PLAIN = F_STATIC | F_BF16;                      // bias only, bf16 out (in_proj of the CLIP tower)
 constexpr int V_LIN1Q = F_STATIC | F_BF16 | F_GELU | F_QUICK;   // c_fc + QuickGELU of the CLIP tower
+constexpr int V_LIN1T = V_LIN1 | F_PRODUCER;                    // lin1 of the training forward: also stores the pre-activation
+constexpr int V_DGELU = F_STATIC | F_BF16 | F_DGELU;            // backward of lin2 into the GELU: acc * gelu'(h) -> bf16
+constexpr int V_F32 = F_STATIC;                                 // plain fp32 out (dX GEMMs of the backward pass)
 constexpr int V_ANY = F_PRODUCER | F_CONSUMER | F_RARE;         // run-time epilogue type, every feature
 template <typename... Args>
 static int launch_variant(bool pair, int feat, Args&&... args) {
@@ -613,6 +660,9 @@ static int launch_variant(bool pair, int feat, Args&&... args) {
             case V_LIN2: return launch_kernel<true, V_LIN2>(args...);
             case V_PLAIN: return launch_kernel<true, V_PLAIN>(args...);
             case V_LIN1Q: return launch_kernel<true, V_LIN1Q>(args...);
+            case V_LIN1T: return launch_kernel<true, V_LIN1T>(args...);
+            case V_DGELU: return launch_kernel<true, V_DGELU>(args...);
+            case V_F32: return launch_kernel<true, V_F32>(args...);
             default: return launch_kernel<true, V_ANY>(args...);
         }
     }
@@ -623,6 +673,9 @@ static int launch_variant(bool pair, int feat, Args&&... args) {
         case V_LIN2: return launch_kernel<false, V_LIN2>(args...);
         case V_PLAIN: return launch_kernel<false, V_PLAIN>(args...);
         case V_LIN1Q: return launch_kernel<false, V_LIN1Q>(args...);
+        case V_LIN1T: return launch_kernel<false, V_LIN1T>(args...);
+        case V_DGELU: return launch_kernel<false, V_DGELU>(args...);
+        case V_F32: return launch_kernel<false, V_F32>(args...);
         default: return launch_kernel<false, V_ANY>(args...);
     }
 }
@@ -677,10 +730,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         tA2 = tA1;
         tB2 = tB1;
     }
-    if ((a.copy_bf16 || a.stat_out) && a.out_bf16)
-        return set_error(CVLM_ERR_ARG, "gemm: bf16 copy / row statistics need the fp32 output path");
-    if (a.copy_bf16 && ((reinterpret_cast<uintptr_t>(a.copy_bf16) & 7) || (a.ldc % 4)))
-        return set_error(CVLM_ERR_ARG, "gemm: bf16 copy must allow 8-byte vectors");
+    if (a.stat_out && a.out_bf16)
+        return set_error(CVLM_ERR_ARG, "gemm: row statistics need the fp32 output path");
+    if (a.copy_bf16 && ((reinterpret_cast<uintptr_t>(a.copy_bf16) & (a.out_bf16 ? 15 : 7)) || (a.ldc % (a.out_bf16 ? 8 : 4))))
+        return set_error(CVLM_ERR_ARG, "gemm: bf16 copy must allow 8-byte (fp32 path) / 16-byte (bf16 path) vectors");
+    if (a.aux && (!a.out_bf16 || (reinterpret_cast<uintptr_t>(a.aux) & 15) || (a.ldaux % 8) || a.act_gelu))
+        return set_error(CVLM_ERR_ARG, "gemm: the gelu' epilogue needs bf16 output, a 16-byte aligned aux and no activation");
     if (a.copy_bf16 && (a.copy_bf16 == a.a1 || a.copy_bf16 == a.a2))
         return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
     if (a.stat_out && a.stat_groups != (a.n + EPI_COLS - 1) / EPI_COLS)
@@ -691,7 +746,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
                static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
                reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
-               a.act_abs, a.conv_pitch, n_run};
+               a.act_abs, a.conv_pitch, n_run, static_cast<const __nv_bfloat16*>(a.aux), a.ldaux};
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     const int tiles_n = (a.n + n_run - 1) / n_run;      // n_run == BN except for narrow outputs / few-tile problems
     const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;
@@ -699,10 +754,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const int total_tiles = nbatch * tiles_m * tiles_n;
     // the exact shape of this call's epilogue; launch_variant maps the four block GEMMs to their own kernels
     const bool rare = nbatch > 1 || a.act_abs || a.res_row_mod > 0 || a.conv_pitch > 0;
-    const bool producer = a.copy_bf16 != nullptr && a.stat_out != nullptr;
+    const bool producer = a.out_bf16 ? a.copy_bf16 != nullptr : (a.copy_bf16 != nullptr && a.stat_out != nullptr);
     int feat = F_STATIC | (a.out_bf16 ? F_BF16 : 0) | (a.act_gelu ? F_GELU : 0) | (a.act_gelu == 2 ? F_QUICK : 0) | (a.residual ? F_RES : 0) |
-               (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0);
-    if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || !a.bias || n_run < BN) feat = V_ANY;
+               (producer ? F_PRODUCER : 0) | (a.ln_rows ? F_CONSUMER : 0) | (a.aux ? F_DGELU : 0);
+    // bias-free GEMMs have static kernels only for the backward shapes (fp32 out, bf16 out, gelu'); the rest read the
+    // epilogue type at run time
+    const bool no_bias_ok = feat == V_F32 || feat == V_PLAIN || feat == V_DGELU;
+    if (rare || (!producer && (a.copy_bf16 || a.stat_out)) || (!a.bias && !no_bias_ok) || n_run < BN) feat = V_ANY;
     return launch_variant(pair, feat, total_tiles, stream, tA1, tB1, tA2, tB2, kb1, kb2, a.m, a.n, nbatch * tiles_m, tiles_n, ep);
 }
 

@@ -9,7 +9,9 @@ and name filters such as ``"prompt_generator" in name`` (train_ovcos_maskdecoder
 working.  They carry no compute: the product path never calls them.
 
 There is no CPU path and no PyTorch fallback: ``forward`` raises if the input is not on a CUDA
-device or if the library has not been built.  ``forward_check`` is the explicit fp32 torch check
+device or if the library has not been built.  With grad mode on and only ``prompt_generator.*`` parameters
+requiring grad (the reference's training configuration, train_ovcos_maskdecoder_edge.py:301-303) ``forward`` is
+differentiable with respect to those parameters (camouflaged_vlm_b200/backward.py).  ``forward_check`` is the explicit fp32 torch check
 path (check_path.py), for parity testing only.
 """
 import ctypes as C
@@ -198,7 +200,11 @@ class ImageEncoderViT(nn.Module):
         self._workspace: Optional[torch.Tensor] = None
         self._stage = None             # forward_host: two device staging buffers + a copy stream
         self._copy_stream = None
+        self._packed_bwd = None        # adapter training: transposed weight copies, backward workspace
+        self._packed_bwd_key = None
+        self._workspace_bwd = None
         self.last_launch_count = 0
+        self.last_backward_launch_count = 0
 
     # ------------------------------------------------------------------ packed-weight cache
     @property
@@ -233,7 +239,8 @@ class ImageEncoderViT(nn.Module):
                                                        t.numel() * t.element_size()), f"set_tensor({name})")
             self._packed_key = key
 
-    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspace", "_stage", "_copy_stream")
+    _RUNTIME_FIELDS = ("_handle", "_packed", "_packed_key", "_workspace", "_stage", "_copy_stream", "_packed_bwd",
+                       "_packed_bwd_key", "_workspace_bwd")
 
     def __getstate__(self):
         # copy.deepcopy / pickle must not share the native handle or the device caches
@@ -263,11 +270,29 @@ class ImageEncoderViT(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("ImageEncoderViT (B200): the encoder only runs on a CUDA device; "
                                "there is no CPU fallback (use forward_check for the fp32 torch check path)")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise RuntimeError("ImageEncoderViT (B200) is forward-only: call it under torch.no_grad() "
-                               "(adapter training needs the reference module; see DESIGN.md, out of scope)")
         if x.dim() != 4 or x.shape[1] != cfg.in_chans or x.shape[2] != cfg.img_size or x.shape[3] != cfg.img_size:
             raise ValueError(f"expected input [B, {cfg.in_chans}, {cfg.img_size}, {cfg.img_size}], got {tuple(x.shape)}")
+        if torch.is_grad_enabled():
+            if x.requires_grad:
+                raise RuntimeError("ImageEncoderViT (B200): no gradient with respect to the input image is implemented "
+                                   "(detach the input; only prompt_generator.* parameters are trainable)")
+            trainable = [n for n, p in self.named_parameters() if p.requires_grad]
+            trunk = [n for n in trainable if "prompt_generator" not in n]
+            if trainable and not trunk:
+                return self._forward_trainable(x, interm)      # adapter-only training
+            if trunk and self.training:
+                raise RuntimeError(
+                    "ImageEncoderViT (B200) trains the adapter only: freeze the trunk the way the reference's training "
+                    "script does (train_ovcos_maskdecoder_edge.py:301-303: requires_grad_(False) for every encoder "
+                    f"parameter without 'prompt_generator' in its name; {len(trunk)} such parameters still require grad, "
+                    f"e.g. {trunk[0]}), or call under torch.no_grad() / .eval() for inference")
+            if trunk:
+                # eval() without no_grad(): the reference would build a graph nobody uses; here the result is detached
+                # (Python's default warning filter shows this once per call site)
+                import warnings
+                warnings.warn("ImageEncoderViT (B200): parameters of the frozen trunk still have requires_grad=True; "
+                              "running inference, the output is detached (no gradient will reach this module)",
+                              stacklevel=2)
         with torch.no_grad():
             x = x.detach().to(torch.float32).contiguous()
             B, g, D = x.shape[0], cfg.grid, cfg.embed_dim
@@ -278,6 +303,35 @@ class ImageEncoderViT(nn.Module):
         if interm:
             return out, [t.permute(0, 3, 1, 2) for t in interms]     # views, like image_encoder.py:148
         return out
+
+    def _forward_trainable(self, x: torch.Tensor, interm: bool):
+        """Differentiable forward: gradients for the ``prompt_generator.*`` parameters (camouflaged_vlm_b200/backward.py)."""
+        from .backward import EncoderTrainFunction, adapter_parameter_names
+        params = dict(self.named_parameters())
+        res = EncoderTrainFunction.apply(self, x, *[params[n] for n in adapter_parameter_names(self._cfg)])
+        out, interms = res[0], res[1:]
+        if interm:
+            return out, [t.permute(0, 3, 1, 2) for t in interms]     # views, like image_encoder.py:148
+        return out
+
+    def _ensure_backward_ready(self, device: torch.device) -> None:
+        """Registers the transposed weight copies the backward pass needs (1.3 GB for ViT-H), once per packing."""
+        if self._packed_bwd_key == self._packed_key and self._packed_bwd is not None:
+            return
+        from .backward import pack_backward_weights
+        lib = _lib.load()
+        self._packed_bwd = pack_backward_weights(dict(self.state_dict()), self._cfg, device, self._packed)
+        for name, t in self._packed_bwd.items():
+            _lib.check(lib.cvlm_encoder_set_tensor(self._handle, name.encode(), t.data_ptr(),
+                                                   t.numel() * t.element_size()), f"set_tensor({name})")
+        self._packed_bwd_key = self._packed_key
+
+    def _get_backward_workspace(self, need: int, device) -> torch.Tensor:
+        ws = self._workspace_bwd
+        if ws is None or ws.numel() < need or ws.device != device:
+            self._workspace_bwd = None
+            self._workspace_bwd = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._workspace_bwd
 
     def _run(self, x: torch.Tensor, out: torch.Tensor, interms: List[torch.Tensor]) -> None:
         """One or more C-ABI calls (chunks of ``max_chunk`` images) writing into caller-provided device tensors:

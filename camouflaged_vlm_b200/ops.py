@@ -196,3 +196,62 @@ def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> tor
                                                  out.data_ptr(), batch, tokens, dim, rank, rank_pad,
                                                  _lib.stream_ptr()), "cvlm_op_adapter_embed")
     return out
+
+
+# ------------------------------------------------------------------ backward-pass kernels (adapter-only training)
+@_on_tensor_device
+def attention_backward(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, rel_pos_h: torch.Tensor,
+                       rel_pos_w: torch.Tensor, batch: int, grid: int, window: int, heads: int, head_dim: int) -> torch.Tensor:
+    """d(loss)/d(qkv) (bf16 [batch*grid^2, 3*D]) of ``attention`` given ``o`` (its output) and ``dout``."""
+    for t in (qkv, o, dout, rel_pos_h, rel_pos_w):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    rows = batch * grid * grid
+    dqkv = torch.zeros_like(qkv)
+    lse = torch.empty(rows, heads, device=qkv.device, dtype=torch.float32)
+    dsum = torch.empty_like(lse)
+    _lib.check(_lib.load().cvlm_op_attention_backward(qkv.data_ptr(), o.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                                                      lse.data_ptr(), dsum.data_ptr(), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(),
+                                                      batch, grid, window, heads, head_dim, _lib.stream_ptr()),
+               "cvlm_op_attention_backward")
+    return dqkv
+
+
+@_on_tensor_device
+def ln_bwd(kind: int, g: torch.Tensor, xsrc: torch.Tensor, stat: Optional[torch.Tensor] = None,
+           gamma: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, eps: float = 1e-6):
+    """LayerNorm backward (csrc/backward.cu).  Returns (dx fp32, bf16 copy)."""
+    rows, cols = g.shape
+    assert g.dtype == torch.float32 and g.is_contiguous() and xsrc.is_contiguous()
+    dx = torch.empty_like(g)
+    dxb = torch.empty(rows, cols, device=g.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_ln_bwd(kind, g.data_ptr(), _ptr(gamma), xsrc.data_ptr(), _ptr(stat), _ptr(residual),
+                                          dx.data_ptr(), dxb.data_ptr(), rows, cols, eps, _lib.stream_ptr()), "cvlm_op_ln_bwd")
+    return dx, dxb
+
+
+@_on_tensor_device
+def wgrad_tn(a: torch.Tensor, b: torch.Tensor, ones: bool = False) -> torch.Tensor:
+    """out[i, j] = sum_m a[m, i] * b[m, j]  (fp32 [I, jp]; column J holds sum_m a[m, i] when ``ones``)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    m, i_cols = a.shape
+    j_cols = b.shape[1]
+    lib = _lib.load()
+    jp, splits = lib.cvlm_op_wgrad_tn_jp(j_cols, int(ones)), lib.cvlm_op_wgrad_tn_splits(m)
+    scratch = torch.empty(splits, i_cols, jp, device=a.device, dtype=torch.float32)
+    out = torch.empty(i_cols, jp, device=a.device, dtype=torch.float32)
+    _lib.check(lib.cvlm_op_wgrad_tn(a.data_ptr(), a.stride(0), i_cols, b.data_ptr(), b.stride(0), j_cols, int(ones), m,
+                                    scratch.data_ptr(), out.data_ptr(), _lib.stream_ptr()), "cvlm_op_wgrad_tn")
+    return out
+
+
+@_on_tensor_device
+def gemm_bf16_dgelu(a: torch.Tensor, b: torch.Tensor, aux: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+    """(a @ b.T) * gelu'(aux), bf16 out (the backward of a Linear -> GELU pair into the GELU's input)."""
+    assert a.dtype == b.dtype == aux.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1 and aux.stride(1) == 1
+    m, k = a.shape
+    n = n or (b.shape[0] + 7) // 8 * 8
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().cvlm_op_gemm_bf16_dgelu(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), k, m, n, b.shape[0],
+                                                   aux.data_ptr(), aux.stride(0), out.data_ptr(), out.stride(0),
+                                                   _lib.stream_ptr()), "cvlm_op_gemm_bf16_dgelu")
+    return out

@@ -118,8 +118,59 @@ int cvlm_encoder_set_profiling(cvlm_encoder* enc, int enable);
 int cvlm_encoder_get_profile(cvlm_encoder* enc, float* ms_by_kind, int* launches_by_kind);
 
 /* ------------------------------------------------------------------------------------------------
+ * Adapter-only training.  The reference trains `prompt_generator.*` with every other encoder
+ * parameter frozen (train_ovcos_maskdecoder_edge.py:301-303); autograd carries the gradient through all blocks
+ * (models/sam_maskdecoder_edge.py:429-460: loss.backward() through self.image_encoder(input, interm=True)).
+ * These two calls replace that autograd graph: the training forward is the inference schedule that also keeps the
+ * activations the backward pass needs in a caller-provided `saved` region (3.4 GB per ViT-H image), the backward pass
+ * turns d(loss)/d(embedding) [and d(loss)/d(interm_k)] into the gradients of the adapter tensors.
+ * Extra tensors to register before cvlm_encoder_backward (bf16, transposed copies of the frozen weights):
+ *   blk.<i>.lin2.wt [4D, D], blk.<i>.lin1.wt [D, 4D] (norm2 gamma folded), blk.<i>.proj.wt [D, D],
+ *   blk.<i>.qkv.wt [D, 3D] (transpose of blk.<i>.qkv.w), neck.conv1.wt [D, out], neck.conv2.wt [out, 9*out]
+ *   (flipped taps), shared.wt [rank_pad, D], lw.wt [rank_pad, depth*rank_pad].
+ * Gradient buffer (fp32, cvlm_encoder_grad_floats floats; cvlm_encoder_grad_layout gives the 5 offsets and jp):
+ *   [0] shared  [D, jp]             cols < rank: d shared_mlp.weight[d, r];  col rank_pad: d shared_mlp.bias[d]
+ *   [1] lw      [depth*rank_pad, jp] row i*rank_pad+s, col r: d lightweight_mlp_i.weight[s, r]; col rank_pad: bias
+ *   [2] hand    [3*16*16, jp]        row k, col r: d prompt_generator.proj.weight[r, k]
+ *   [3] dtsum   [rank_pad, jp]       col rank_pad, row r: d prompt_generator.proj.bias[r] = d embedding_generator.bias[r]
+ *   [4] eg      [D, rank_pad]        d embedding_generator.weight[r, d] transposed
+ * dout_nhwc: fp32 [batch*T, out_chans] (d loss / d embedding, channels last); dinterm_nhwc: NULL or one fp32
+ * [batch*T, D] pointer (or NULL) per global block.
+ * ---------------------------------------------------------------------------------------------- */
+long long cvlm_encoder_saved_bytes(const cvlm_encoder* enc, int batch);
+long long cvlm_encoder_backward_workspace_bytes(const cvlm_encoder* enc, int batch);
+long long cvlm_encoder_grad_floats(const cvlm_encoder* enc);
+int cvlm_encoder_grad_layout(const cvlm_encoder* enc, long long* offsets5, int* jp);
+int cvlm_encoder_forward_train(cvlm_encoder* enc, const float* images, int batch, float* out, float* const* interm,
+                               void* saved, long long saved_bytes, void* workspace, long long workspace_bytes,
+                               cvlm_stream_t stream);
+int cvlm_encoder_backward(cvlm_encoder* enc, int batch, const float* dout_nhwc, const float* const* dinterm_nhwc,
+                          const void* saved, long long saved_bytes, float* grads, long long grads_floats, void* workspace,
+                          long long workspace_bytes, cvlm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Op-level entry points (the kernels behind the encoder; used by the parity tests and profiling).
  * ---------------------------------------------------------------------------------------------- */
+
+/* Backward of cvlm_op_attention: dqkv (bf16 [batch*G*G, 3*D]) from qkv, the forward output o and dout (bf16
+ * [batch*G*G, D]); lse / dsum: fp32 [batch*G*G, heads] scratch (row log-sum-exp, rowsum(dout*o)).  mma.sync kernels. */
+int cvlm_op_attention_backward(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
+                               const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side, int window,
+                               int heads, int head_dim, cvlm_stream_t stream);
+/* LayerNorm backward, one warp per row: dx = (residual ? residual : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),
+ * g = gin * gamma (gamma NULL: already folded).  xhat_kind 0: xsrc = raw bf16 x, stat = (rstd, -mean*rstd) rows;
+ * 1: xsrc = bf16 xhat, stat = rstd rows; 2: xsrc = fp32 x, statistics recomputed with eps.  dxb (optional) = bf16(dx). */
+int cvlm_op_ln_bwd(int xhat_kind, const float* gin, const float* gamma, const void* xsrc, const float* stat,
+                   const float* residual, float* dx, void* dxb, long long rows, int cols, float eps, cvlm_stream_t stream);
+/* Weight gradient out[i, j] = sum_m A[m, i] * B[m, j] (+ column J = sum_m A[m, i] when ones != 0): A bf16 [m, I], B bf16
+ * [m, J]; out fp32 [I, jp] with jp = cvlm_op_wgrad_tn_jp(J, ones); scratch fp32 [cvlm_op_wgrad_tn_splits(m), I, jp]. */
+int cvlm_op_wgrad_tn_jp(int j, int ones);
+int cvlm_op_wgrad_tn_splits(long long m);
+int cvlm_op_wgrad_tn(const void* a, long long lda, int i_cols, const void* b, long long ldb, int j_cols, int ones,
+                     long long m, float* scratch, float* out, cvlm_stream_t stream);
+/* cvlm_op_gemm_bf16 with the backward-of-GELU epilogue: out (bf16) = (A * B^T) * gelu'(aux[row, col]), aux bf16 [m, ldaux]. */
+int cvlm_op_gemm_bf16_dgelu(const void* a, long long lda, const void* b, long long ldb, int k, int m, int n, int b_rows,
+                            const void* aux, long long ldaux, void* out, long long ldo, cvlm_stream_t stream);
 
 /* out = epilogue(A1 * B1^T [+ A2 * B2^T]); A* bf16 [m, k*] row stride lda*, B* bf16 [b_rows, k*] row
  * stride ldb* (weights, nn.Linear layout), rows >= b_rows read as zero.  Epilogue: + bias[n] (fp32),

@@ -147,12 +147,12 @@ def prompts(sd: Dict[str, Tensor], cfg, x_patch: Tensor, inp: Tensor) -> List[Te
     return out
 
 
-@torch.no_grad()
-def encoder_forward(sd: Dict[str, Tensor], cfg, x: Tensor, interm: bool = False, ln_eps: float = 1e-6,
-                    stop_after_block: int = -1):
+def encoder_forward_autograd(sd: Dict[str, Tensor], cfg, x: Tensor, interm: bool = False, ln_eps: float = 1e-6,
+                             stop_after_block: int = -1):
     """ImageEncoderViT.forward, image_encoder.py:132-155.  ``ln_eps`` is the eps the callers bind
     into norm_layer (models/sam_maskdecoder_edge.py:129).  ``stop_after_block`` >= 0 returns the
-    NHWC residual stream after that block (debug aid for per-layer parity)."""
+    NHWC residual stream after that block (debug aid for per-layer parity).  Plain torch ops: differentiable
+    (``adapter_gradients``); ``encoder_forward`` is the same function under ``torch.no_grad()``."""
     inp = x
     g = cfg.grid
     xp = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"],
@@ -173,6 +173,37 @@ def encoder_forward(sd: Dict[str, Tensor], cfg, x: Tensor, interm: bool = False,
     y = F.conv2d(y, sd["neck.2.weight"], padding=1)
     y = layer_norm_2d(y, sd["neck.3.weight"], sd["neck.3.bias"])
     return (y, interms) if interm else y
+
+
+encoder_forward = torch.no_grad()(encoder_forward_autograd)
+
+
+def cotangents(cfg, batch: int, seed: int = 0) -> Tuple[Tensor, List[Tensor]]:
+    """Seeded d(loss)/d(output) tensors for gradient parity: loss = sum(out * c) + sum_k sum(interm_k * c_k)."""
+    from camouflaged_vlm_b200.synth import _normal
+    g = cfg.grid
+    c_out = torch.from_numpy(_normal("cotangent.out", (batch, cfg.out_chans, g, g), seed))
+    c_int = [torch.from_numpy(_normal(f"cotangent.interm{k}", (batch, cfg.embed_dim, g, g), seed)) * 0.05
+             for k in range(len(cfg.global_attn_indexes))]
+    return c_out, c_int
+
+
+def adapter_gradients(sd: Dict[str, Tensor], cfg, x: Tensor, c_out: Tensor, c_interm: List[Tensor] = None,
+                      ln_eps: float = 1e-6) -> Dict[str, Tensor]:
+    """Gradients of  sum(out * c_out) [+ sum_k sum(interm_k * c_interm[k])]  with respect to every
+    ``prompt_generator.*`` parameter, everything else frozen -- the training configuration of the reference
+    (train_ovcos_maskdecoder_edge.py:301-303: only names without "image_encoder" or with "prompt_generator" train;
+    the gradient reaches the adapter through all blocks, models/sam_maskdecoder_edge.py:429-460)."""
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k.startswith("prompt_generator.") else v.detach())
+            for k, v in sd.items()}
+    use_interm = bool(c_interm)
+    res = encoder_forward_autograd(leaf, cfg, x, interm=use_interm, ln_eps=ln_eps)
+    out, interms = res if use_interm else (res, [])
+    loss = (out * c_out).sum()
+    for t, c in zip(interms, c_interm or []):
+        loss = loss + (t * c).sum()
+    loss.backward()
+    return {k: v.grad for k, v in leaf.items() if k.startswith("prompt_generator.")}
 
 
 def rel_l2(a: Tensor, ref: Tensor) -> float:

@@ -86,10 +86,13 @@ def test_encoder_vit_h_matches_reference_golden():
     with torch.no_grad():
         outb = m(xb)
         outb2 = m(xb)
+        out1 = m(x)                                       # same schedule (interm=False folds the prompt at every block)
     assert torch.equal(outb, outb2)                       # run-to-run deterministic
     # no cross-image state and the same summation order per output element whatever the batch / chunking: the image's
-    # embedding is bit-identical to its batch-1 result (the batch-32 case is tests/test_gpu_parity_b32.py)
-    assert torch.equal(outb[1:2], out)
+    # embedding is bit-identical to its batch-1 result (the batch-32 case is tests/test_gpu_parity_b32.py); the
+    # interm=True schedule rounds differently at the global blocks and agrees to the bf16 noise floor
+    assert torch.equal(outb[1:2], out1)
+    assert orc.rel_l2(out1, out) < BF16_TOL
 
 
 def test_downstream_mask_iou_vit_h():
@@ -124,13 +127,21 @@ def test_state_dict_round_trip_and_reload():
     assert torch.equal(a, c)
 
 
-def test_forward_refuses_cpu_and_grad():
+def test_forward_refuses_cpu_and_unsupported_grad_requests():
     cfg = PRESETS["tiny"]
     m = _encoder(cfg)
     with pytest.raises(RuntimeError):
         m(seeded_images(cfg, 1))                                       # CPU tensor: no fallback
-    with pytest.raises(RuntimeError):
-        m(seeded_images(cfg, 1).cuda())                                # grad mode: forward-only
+    x = seeded_images(cfg, 1).cuda()
+    with pytest.warns(UserWarning, match="detached"):                  # eval() without no_grad(), like the reference
+        out = m(x)                                                     # allows: runs inference, result detached
+    assert not out.requires_grad
+    with pytest.raises(RuntimeError, match="input"):
+        m(x.clone().requires_grad_(True))                              # no input gradient
+    m.train()
+    with pytest.raises(RuntimeError, match="prompt_generator"):        # trunk gradients do not exist: says how to freeze
+        m(x)
+    # (the adapter-only training path itself: tests/test_gpu_backward.py)
 
 
 def test_encoder_vit_b_full_geometry_against_oracle():

@@ -106,3 +106,17 @@ class TestAgainstLiveReference:
         with torch.no_grad():
             want = ref(x)
         assert orc.rel_l2(orc.encoder_forward(sd, cfg, x), want) < FP32_TOL
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 2), ("small_hd80", 1), ("small_hd64", 1)])
+def test_oracle_adapter_gradients_match_reference_autograd(name, batch):
+    """the gradients of every prompt_generator.* tensor through the oracle (torch autograd over the
+    functional restatement) equal the UNMODIFIED reference's under the training script's freeze rule
+    (tests/golden/encoder_grads_*.npz, oracle/make_golden_grads.py)."""
+    cfg = PRESETS[name]
+    gold = np.load(os.path.join(GOLDEN, f"encoder_grads_{name}.npz"))
+    c_out, c_int = orc.cotangents(cfg, batch, 0)
+    grads = orc.adapter_gradients(seeded_state_dict(cfg, 0), cfg, seeded_images(cfg, batch, 0), c_out, c_int)
+    assert set(grads) == set(k for k in gold.files if k != "loss")
+    for k, v in grads.items():
+        assert orc.rel_l2(v, torch.from_numpy(gold[k])) < 1e-4, k
