@@ -242,7 +242,8 @@ int backward_impl(cvlm_encoder* enc, int batch, const float* dout_nhwc, const fl
         CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
     }
     CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_tn_launch(dpre, ldg, static_cast<int>(ldg), svb + sv.off_t, RP, RP, 1, M, p_lw, 0, stream); }));
-    CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_tn_launch(svb + sv.off_php, kp, kp, dt, RP, RP, 0, M, p_hand, 0, stream); }));
+    // (ones column requested only so that every partial of this pass has the same width jp; its content is unused)
+    CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_tn_launch(svb + sv.off_php, kp, kp, dt, RP, RP, 1, M, p_hand, 0, stream); }));
     CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_tn_launch(dt, RP, RP, dt, RP, RP, 1, M, p_dt, 0, stream); }));
     CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_reduce_launch(p_shared, ws.splits, static_cast<long long>(D) * gl.jp, grads + gl.off_shared, stream); }));
     CVLM_TRY(f.run(K_OTHER, [&] { return wgrad_reduce_launch(p_lw, ws.splits, ldg * gl.jp, grads + gl.off_lw, stream); }));

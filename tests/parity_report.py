@@ -133,6 +133,57 @@ def main(out_path):
     a, b = high_pass(x, 0.25)[1:2], high_pass(x[1:2], 0.25)
     rep["high_pass_batch_dependence_max_abs"] = float((a - b).abs().max())
     print("high_pass batch dependence max abs:", rep["high_pass_batch_dependence_max_abs"])
+    # ---- BASELINE.json configs[1] north-star lines: fp32 check path at ViT-H, and the mask-IoU probe next to what the
+    # REFERENCE ITSELF gives in bf16 (torch.autocast) and in fp32 on this GPU -- the probe's noise floor
+    m = build_encoder(cfg).eval()
+    m.load_state_dict(seeded_state_dict(cfg), strict=True)
+    m = m.cuda()
+    gm = np.load(os.path.join(GOLDEN, "encoder_vit_h_multi.npz"))
+    stride = int(gm["stride"])
+    n_img = 4
+    imgs = seeded_images(cfg, n_img, 0).cuda()
+    with torch.no_grad():
+        chk = torch.cat([m.forward_check(imgs[i:i + 1]) for i in range(n_img)])
+        ours = m(imgs)
+    ref_sub = torch.from_numpy(gm["out_sub"][:n_img])
+    vit_h = {"fp32_check_path_rel_l2_vs_reference": [orc.rel_l2(chk[i, :, ::stride, ::stride].cpu(), ref_sub[i]) for i in range(n_img)],
+             "bf16_path_rel_l2_vs_reference": [orc.rel_l2(ours[i, :, ::stride, ::stride].cpu(), ref_sub[i]) for i in range(n_img)]}
+    embs = {"ours_bf16": ours.cpu(), "ours_fp32_check_path": chk.cpu()}
+    del m
+    torch.cuda.empty_cache()
+    from oracle import ref_import
+    if ref_import.staged_encoder_available():
+        ref = ref_import.build_reference_encoder(cfg, staged=True).eval()
+        ref.load_state_dict(seeded_state_dict(cfg), strict=True)
+        ref = ref.cuda()
+        with torch.no_grad():
+            r32 = torch.cat([ref(imgs[i:i + 1]) for i in range(n_img)])
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                r16 = torch.cat([ref(imgs[i:i + 1]).float() for i in range(n_img)])
+        vit_h["reference_gpu_fp32_rel_l2_vs_reference_cpu"] = [orc.rel_l2(r32[i, :, ::stride, ::stride].cpu(), ref_sub[i]) for i in range(n_img)]
+        vit_h["reference_autocast_bf16_rel_l2_vs_reference_cpu"] = [orc.rel_l2(r16[i, :, ::stride, ::stride].cpu(), ref_sub[i]) for i in range(n_img)]
+        embs["reference_gpu_fp32"] = r32.cpu()
+        embs["reference_autocast_bf16"] = r16.cpu()
+        del ref
+        torch.cuda.empty_cache()
+    probe = {}
+    for label, e in embs.items():
+        per_seed = []
+        for sdx in range(gm["logits"].shape[0]):
+            dsd_s = mdo.seeded_decoder_state(sdx)
+            vals = []
+            for i in range(n_img):
+                got = mdo.decode_mask_logits(dsd_s, e[i:i + 1])
+                want_l = torch.from_numpy(gm["logits"][sdx, i].astype(np.float32))[None, None]
+                vals.append(mdo.iou(mdo.binary_mask(got, 1024), mdo.binary_mask(want_l, 1024)))
+            per_seed.append({"decoder_seed": sdx, "iou_min": min(vals), "iou_mean": sum(vals) / len(vals)})
+        probe[label] = per_seed
+    vit_h["mask_iou_probe_vs_reference_cascade"] = probe
+    vit_h["note"] = ("IoU of the binary masks of a RANDOM-INIT MaskDecoder_Edge (3 seeds) on each encoder's embedding against the "
+                     "reference CPU fp32 cascade, 4 images; the value is set by the decoder draw (how many pixels have a logit "
+                     "within the embedding's noise), not by the image")
+    rep["vit_h_north_star"] = vit_h
+    print("vit_h north star:", json.dumps(vit_h))
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     json.dump(rep, open(out_path, "w"), indent=1)
 
