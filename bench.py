@@ -547,6 +547,63 @@ def run_ours(args):
         del tw
         torch.cuda.empty_cache()
 
+    # ---- one adapter-only training step (the reference's training configuration: every encoder parameter
+    # frozen except prompt_generator.*, train_ovcos_maskdecoder_edge.py:301-303) -- training forward that keeps the
+    # activations + backward pass to the 70 adapter gradients, through loss.backward() on the nn.Module
+    f4 = None
+    if rank == 0 and world == 1 and not args.skip_train:
+        tb = min(8, B)
+        try:
+            for n, p in model.named_parameters():
+                p.requires_grad_("prompt_generator" in n)
+            model.train()
+            xt = x_dev[:tb]
+            cot = torch.randn(tb, cfg.out_chans, cfg.grid, cfg.grid, device=dev)
+            adapter = [p for p in model.parameters() if p.requires_grad]
+
+            def train_step():
+                for p in adapter:
+                    p.grad = None
+                o, _ = model(xt, interm=True)
+                (o * cot).sum().backward()
+
+            for _ in range(2):
+                train_step()
+            torch.cuda.synchronize()
+            n_t = 4
+            e0.record()
+            for _ in range(n_t):
+                train_step()
+            e1.record()
+            torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / n_t
+            with torch.no_grad():
+                model.eval()
+                for _ in range(2):
+                    model(xt, interm=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(n_t):
+                    model(xt, interm=True)
+                e1.record()
+                torch.cuda.synchronize()
+            f_ms = e0.elapsed_time(e1) / n_t
+            saved_gb = _lib.check(lib.cvlm_encoder_saved_bytes(model._handle, tb)) / 1e9
+            f4 = {"metric": "adapter_train_step_img_per_s", "value": tb / t_ms * 1e3, "unit": UNIT, "ms_per_step": t_ms,
+                  "batch": tb, "inference_forward_ms_same_batch": f_ms, "step_over_forward": t_ms / f_ms,
+                  "gpu_launches": int(model.last_launch_count + model.last_backward_launch_count),
+                  "saved_activations_gb": saved_gb, "grads_finite": bool(all(torch.isfinite(p.grad).all() for p in adapter)),
+                  "workload": f"forward_train + backward of {tb} ViT-H images (gradients of the {len(adapter)} "
+                              "prompt_generator tensors, trunk frozen), loss = <embedding, fixed cotangent>"}
+        except torch.cuda.OutOfMemoryError:
+            f4 = {"unavailable": "out of memory"}
+        finally:
+            model.eval()
+            for p in model.parameters():
+                p.requires_grad_(True)
+            model._workspace_bwd = None
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline beside it (rank 0, single-GPU run only): the reference module itself (oracle/_ref/refsam) when
     # staged, else the oracle port, with THIS run's weights; its embedding of the timed image is kept and compared with
     # the CUDA encoder's on the same image -> `parity` (north_star: rel-L2 <= 1e-2)
@@ -581,7 +638,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity, "torch_gpu_baseline": tgb, "gather": gather_info,
-            "kernels": kernels, "mask_decoder": f1, "alpha_clip_tower": f2,
+            "kernels": kernels, "mask_decoder": f1, "alpha_clip_tower": f2, "adapter_training": f4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

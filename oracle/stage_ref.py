@@ -21,17 +21,30 @@ DST_DIR = os.path.join(ROOT, "oracle", "_ref", "refsam")
 FILES = ("image_encoder.py", "common.py")
 
 
+def _copy(src: str, dst: str, verbose: bool) -> None:
+    if not (os.path.isfile(dst) and filecmp.cmp(src, dst, shallow=False)):
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+        if verbose:
+            print(f"[stage_ref] {src} -> {dst}")
+
+
 def stage(verbose: bool = True) -> bool:
-    """Returns True when oracle/_ref/refsam holds the reference files (freshly copied or already identical)."""
+    """Returns True when oracle/_ref/refsam holds the reference files (freshly copied or already identical).  Also stages
+    the files of the whole inference cascade (BASELINE.json configs[3]: wrapper, decoder, Alpha-CLIP, prompt learner,
+    tokenizer vocabulary, class names, shipped text features; list in oracle/ref_cascade.py) under oracle/_ref/cascade,
+    mirroring the reference tree, for the swapped-vs-not test on the GPU box."""
     if not all(os.path.isfile(os.path.join(SRC_DIR, f)) for f in FILES):
         return all(os.path.isfile(os.path.join(DST_DIR, f)) for f in FILES)
-    os.makedirs(DST_DIR, exist_ok=True)
     for f in FILES:
-        src, dst = os.path.join(SRC_DIR, f), os.path.join(DST_DIR, f)
-        if not (os.path.isfile(dst) and filecmp.cmp(src, dst, shallow=False)):
-            shutil.copyfile(src, dst)
-            if verbose:
-                print(f"[stage_ref] {src} -> {dst}")
+        _copy(os.path.join(SRC_DIR, f), os.path.join(DST_DIR, f), verbose)
+    try:
+        from oracle.ref_cascade import CASCADE_FILES, STAGED_ROOT
+    except ImportError:          # run as a script: oracle/ is sys.path[0]
+        from ref_cascade import CASCADE_FILES, STAGED_ROOT
+    if all(os.path.isfile(os.path.join(REF_ROOT, f)) for f in CASCADE_FILES):
+        for f in CASCADE_FILES:
+            _copy(os.path.join(REF_ROOT, f), os.path.join(STAGED_ROOT, f), verbose)
     return True
 
 
