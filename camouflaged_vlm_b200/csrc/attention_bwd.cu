@@ -682,8 +682,594 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_dkv_kernel(const BwdParam
     }
 }
 
+// ================================================================================================
+// S == 64 on the 64 x 64 grid (the four global blocks of ViT-B/L/H): a query tile is grid row qy, a key tile is grid row
+// ky, every token exists.  The generic kernels above spend half of their mma.sync on the rel-pos bookkeeping there
+// (indicator products in dq, the full 2 x 127-column T recompute per tile pair in dkv) and their 178 KB of shared memory
+// allow one CTA of four warps per SM (measured: 45.7 ms per block for 8 images, 102 TFLOP/s).  Specialised:
+//   * rel_h depends on (qy - ky) only: ONE column of T_h per tile pair.  dq keeps T_h on table rows qy..qy+63 ([64][65]
+//     floats) and dS's row sum over a key tile IS dSh[q][ky]; dkv projects a single table row per query tile (5 mma).
+//   * rel_w: the 64 values of a row are the same for every key tile: gathered into registers once (dq); its gradient is
+//     a per-column register accumulator.
+//   * shared memory is re-used along the kernel (tables <-> K/V double buffer, Q/dO tiles <-> T_h / dSh, T_w <-> dSw):
+//     ~101 KB (dq) / ~104 KB (dkv) -> two CTAs per SM.
+template <int HD>
+struct Bwd64Smem {
+    static constexpr int HDP = HD + 8;
+    static constexpr int KV = 4 * BW_T * HDP * 2;                 // 2 stages x (K | V); also: tables (192 rows) + dQ staging
+    static constexpr int QO = 2 * BW_T * HDP * 2;                 // Q | dO tiles; later T_h / dSh [64][65] fp32
+    static constexpr int TH = BW_T * 65 * 4;
+    static constexpr int TW = BW_T * 129 * 4;                     // T_w [64][129] fp32; later dSw [64][65]
+    static constexpr int DQ_QO = QO > TH ? QO : TH;
+    static constexpr int dq_off_kv = 0, dq_off_qo = KV, dq_off_tw = KV + DQ_QO, dq_off_row = dq_off_tw + TW;
+    static constexpr int dq_total = dq_off_row + 2 * BW_T * 4;
+    // dkv: this CTA's K | V, the query tile's Q | dO, rel_pos_w (128 rows), 16 rows for the one rel_pos_h row, T_w, rows
+    static constexpr int dkv_off_kv = 0, dkv_off_qo = 2 * BW_T * HDP * 2, dkv_off_rw = dkv_off_qo + QO;
+    static constexpr int dkv_off_rh = dkv_off_rw + 128 * HDP * 2, dkv_off_tw = dkv_off_rh + 16 * HDP * 2;
+    static constexpr int dkv_off_row = dkv_off_tw + TW, dkv_total = dkv_off_row + 3 * BW_T * 4;
+    static_assert(192 * HDP * 2 + BW_T * HDP * 2 <= KV, "tables + dQ staging must fit the K/V double buffer");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq64_kernel(const BwdParams p) {
+    using Plan = Bwd64Smem<HD>;
+    constexpr int HDP = Plan::HDP, KSTEPS = HD / 16, DT = HD / 8, CH = HD / 8;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __nv_bfloat16* sKVb = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dq_off_kv);
+    __nv_bfloat16* sTab = sKVb;                                   // [0,64): rel_pos_h rows qt..qt+63, [64,192): rel_pos_w
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dq_off_qo);
+    __nv_bfloat16* sdO = sQ + BW_T * HDP;
+    float* sTh = reinterpret_cast<float*>(smem + Plan::dq_off_qo);   // after the fragments are in registers
+    float* sTw = reinterpret_cast<float*>(smem + Plan::dq_off_tw);
+    float* sRow = reinterpret_cast<float*>(smem + Plan::dq_off_row);
+    constexpr int THS = 65, TWS = 129;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const long long tok_base = static_cast<long long>(b) * 4096;
+    const int ld = 3 * p.D;
+    const __nv_bfloat16* qbase = p.qkv + head * HD;
+    const __nv_bfloat16* kbase = qbase + p.D;
+    const __nv_bfloat16* vbase = qbase + 2 * p.D;
+
+    // ---- prologue: Q, dO, tables; D = rowsum(dO * o)
+    for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const long long tok = tok_base + qt * 64 + r;
+        cp_async_16(smem_u32(sQ + r * HDP + c * 8), qbase + tok * ld + c * 8, true);
+        cp_async_16(smem_u32(sdO + r * HDP + c * 8), p.dout + tok * p.D + head * HD + c * 8, true);
+    }
+    auto stage_tables64 = [&]() {
+        for (int i = tid; i < 192 * CH; i += BW_THREADS) {
+            const int r = i / CH, c = i - r * CH;
+            const bool is_w = r >= 64;
+            const int row = is_w ? r - 64 : qt + r;                 // 2S-1 = 127 rows exist
+            const __nv_bfloat16* tab = is_w ? p.relw : p.relh;
+            cp_async_16(smem_u32(sTab + r * HDP + c * 8), tab + (row < 127 ? row : 0) * HD + c * 8, row < 127);
+        }
+    };
+    stage_tables64();
+    cp_async_commit();
+    {
+        const int r = tid >> 1, half = tid & 1;
+        const long long tok = tok_base + qt * 64 + r;
+        const __nv_bfloat16* po = p.o + tok * p.D + head * HD + half * (HD / 2);
+        const __nv_bfloat16* pd = p.dout + tok * p.D + head * HD + half * (HD / 2);
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(po + c * 8), bb = *reinterpret_cast<const uint4*>(pd + c * 8);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw4[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                d = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(bw4[e] << 16), d);
+                d = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(bw4[e] & 0xffff0000u), d);
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        if (half == 0) {
+            sRow[r] = d;
+            p.dsum[tok * p.heads + head] = d;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t qf[KSTEPS][4], dof[KSTEPS][4];
+    {
+        const int row = warp * 16 + (lane & 15);
+        const int koff = (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            ldmatrix_x4(smem_u32(sQ + row * HDP + ks * 16 + koff), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            ldmatrix_x4(smem_u32(sdO + row * HDP + ks * 16 + koff), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
+        }
+    }
+    const float dD[2] = {sRow[warp * 16 + g], sRow[warp * 16 + g + 8]};
+    __syncthreads();                                   // the Q / dO tiles are dead: their bytes become T_h
+    const int krow = (lane & 7) + ((lane >> 4) << 3);
+    const int kcol = ((lane >> 3) & 1) * 8;
+    // T_h on table rows qt..qt+63 (64 columns), T_w on all 127 (128 columns)
+    for (int which = 0; which < 2; ++which) {
+        const __nv_bfloat16* sR = which ? sTab + 64 * HDP : sTab;
+        float* sT = which ? sTw : sTh;
+        const int ts = which ? TWS : THS, ncols = which ? 128 : 64;
+        for (int n0 = 0; n0 < ncols; n0 += 16) {
+            float acc[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sR + (n0 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(acc[0], qf[ks], b0, b1);
+                mma_bf16_16816(acc[1], qf[ks], b2, b3);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = n0 + h * 8 + 2 * t, r0 = warp * 16 + g;
+                sT[r0 * ts + col] = acc[h][0] * kLog2eB;
+                sT[r0 * ts + col + 1] = acc[h][1] * kLog2eB;
+                sT[(r0 + 8) * ts + col] = acc[h][2] * kLog2eB;
+                sT[(r0 + 8) * ts + col + 1] = acc[h][3] * kLog2eB;
+            }
+        }
+    }
+    __syncwarp();                                      // a warp only reads back its own 16 rows
+    // rel_w[q][kx] = T_w[q][qx - kx + 63], qx = row index inside the tile: the same for every key tile -> registers
+    float twreg[8][4];
+    {
+        const float* tw0 = sTw + (warp * 16 + g) * TWS;
+        const float* tw1 = tw0 + 8 * TWS;
+        const int o0 = warp * 16 + g + 63, o1 = o0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            twreg[nt][0] = tw0[o0 - col];
+            twreg[nt][1] = tw0[o0 - col - 1];
+            twreg[nt][2] = tw1[o1 - col];
+            twreg[nt][3] = tw1[o1 - col - 1];
+        }
+    }
+    float* th0p = sTh + (warp * 16 + g) * THS;
+    float* th1p = th0p + 8 * THS;
+    __syncthreads();                                   // tables dead: the K/V double buffer takes their place
+
+    auto load_tile = [&](int kt, int stage, bool with_v) {
+        __nv_bfloat16* sK = sKVb + stage * 2 * BW_T * HDP;
+        __nv_bfloat16* sV = sK + BW_T * HDP;
+        for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+            const int r = i / CH, c = i - r * CH;
+            const long long row = (tok_base + kt * 64 + r) * ld + c * 8;
+            cp_async_16(smem_u32(sK + r * HDP + c * 8), kbase + row, true);
+            if (with_v) cp_async_16(smem_u32(sV + r * HDP + c * 8), vbase + row, true);
+        }
+    };
+    auto logits64 = [&](const __nv_bfloat16* sK, int kt, float (&s)[8][4]) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sK + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+            }
+        }
+        const float t0 = th0p[63 - kt], t1 = th1p[63 - kt];      // T_h column of table row qt + 63 - kt = qy - ky + 63
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = fmaf(s[nt][0], p.scale_log2, t0 + twreg[nt][0]);
+            s[nt][1] = fmaf(s[nt][1], p.scale_log2, t0 + twreg[nt][1]);
+            s[nt][2] = fmaf(s[nt][2], p.scale_log2, t1 + twreg[nt][2]);
+            s[nt][3] = fmaf(s[nt][3], p.scale_log2, t1 + twreg[nt][3]);
+        }
+    };
+
+    // ---- pass 1: row log-sum-exp (K tiles only)
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    load_tile(0, 0, false);
+    cp_async_commit();
+    for (int kt = 0; kt < 64; ++kt) {
+        const int stage = kt & 1;
+        if (kt + 1 < 64) load_tile(kt + 1, stage ^ 1, false);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        float s[8][4];
+        logits64(sKVb + stage * 2 * BW_T * HDP, kt, s);
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+            const float m_new = fmaxf(m_run[h], mx[h]);
+            l_run[h] *= ex2f(m_run[h] - m_new);
+            m_run[h] = m_new;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            l_run[0] += ex2f(s[nt][0] - m_run[0]) + ex2f(s[nt][1] - m_run[0]);
+            l_run[1] += ex2f(s[nt][2] - m_run[1]) + ex2f(s[nt][3] - m_run[1]);
+        }
+        __syncthreads();
+    }
+    float lse[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+        lse[h] = m_run[h] + log2f(l_run[h]);
+        if (t == 0) p.lse[(tok_base + qt * 64 + warp * 16 + g + h * 8) * p.heads + head] = lse[h];
+    }
+
+    // ---- pass 2
+    float dq[DT][4], dsw[8][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dsw[i][0] = dsw[i][1] = dsw[i][2] = dsw[i][3] = 0.f;
+    load_tile(0, 0, true);
+    cp_async_commit();
+    for (int kt = 0; kt < 64; ++kt) {
+        const int stage = kt & 1;
+        if (kt + 1 < 64) load_tile(kt + 1, stage ^ 1, true);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const __nv_bfloat16* sK = sKVb + stage * 2 * BW_T * HDP;
+        const __nv_bfloat16* sV = sK + BW_T * HDP;
+        float s[8][4];
+        logits64(sK, kt, s);
+        float dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sV + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(dp[2 * np], dof[ks], b0, b1);
+                mma_bf16_16816(dp[2 * np + 1], dof[ks], b2, b3);
+            }
+        }
+        uint32_t dsf[4][4];
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float d0 = ex2f(s[nt][0] - lse[0]) * (dp[nt][0] - dD[0]);
+            const float d1 = ex2f(s[nt][1] - lse[0]) * (dp[nt][1] - dD[0]);
+            const float d2 = ex2f(s[nt][2] - lse[1]) * (dp[nt][2] - dD[1]);
+            const float d3 = ex2f(s[nt][3] - lse[1]) * (dp[nt][3] - dD[1]);
+            rs0 += d0 + d1;
+            rs1 += d2 + d3;
+            dsw[nt][0] += d0; dsw[nt][1] += d1; dsw[nt][2] += d2; dsw[nt][3] += d3;
+            dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(d0, d1);
+            dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(d2, d3);
+        }
+        // dSh[q][ky = kt] = row sum of dS over this key tile; it takes the place of the T_h value just consumed
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        if (t == 0) {
+            th0p[63 - kt] = rs0;
+            th1p[63 - kt] = rs1;
+        }
+        {
+            const int vrow = lane & 15;
+            const int vcol = (lane >> 4) * 8;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(smem_u32(sK + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dq[2 * dpi], dsf[kk], b0, b1);
+                    mma_bf16_16816(dq[2 * dpi + 1], dsf[kk], b2, b3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- rel-pos part of dQ.  Tables come back into the (dead) K/V buffer; dSw goes where T_w was.
+    stage_tables64();
+    cp_async_commit();
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        dq[i][0] *= p.scale; dq[i][1] *= p.scale; dq[i][2] *= p.scale; dq[i][3] *= p.scale;
+    }
+    {
+        float* w0 = sTw + (warp * 16 + g) * THS;            // dSw [64][65]
+        float* w1 = w0 + 8 * THS;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            w0[col] = dsw[nt][0]; w0[col + 1] = dsw[nt][1];
+            w1[col] = dsw[nt][2]; w1[col + 1] = dsw[nt][3];
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    {
+        const int vrow = lane & 15;
+        const int vcol = (lane >> 4) * 8;
+        // h: dT_h[q][table row qt + c] = dSh[q][c]  ->  A = sTh as it is, B = rel_pos_h rows qt..qt+63
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int c0 = kk * 16 + 2 * t;
+            uint32_t af[4];
+            af[0] = pack_bf16(th0p[c0], th0p[c0 + 1]);
+            af[1] = pack_bf16(th1p[c0], th1p[c0 + 1]);
+            af[2] = pack_bf16(th0p[c0 + 8], th0p[c0 + 9]);
+            af[3] = pack_bf16(th1p[c0 + 8], th1p[c0 + 9]);
+#pragma unroll
+            for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(smem_u32(sTab + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                mma_bf16_16816(dq[2 * dpi], af, b0, b1);
+                mma_bf16_16816(dq[2 * dpi + 1], af, b2, b3);
+            }
+        }
+        // w: dT_w[q][j] = dSw[q][qx + 63 - j] (0 outside [0, 64))
+        const float* w0 = sTw + (warp * 16 + g) * THS;
+        const float* w1 = w0 + 8 * THS;
+        const int o0 = warp * 16 + g + 63, o1 = o0 + 8;
+        auto pick = [&](const float* row, int off, int j) -> float {
+            const int x = off - j;
+            return (x >= 0 && x < 64) ? row[x] : 0.f;
+        };
+#pragma unroll 2
+        for (int kk = 0; kk < 8; ++kk) {
+            const int j0 = kk * 16 + 2 * t;
+            uint32_t af[4];
+            af[0] = pack_bf16(pick(w0, o0, j0), pick(w0, o0, j0 + 1));
+            af[1] = pack_bf16(pick(w1, o1, j0), pick(w1, o1, j0 + 1));
+            af[2] = pack_bf16(pick(w0, o0, j0 + 8), pick(w0, o0, j0 + 9));
+            af[3] = pack_bf16(pick(w1, o1, j0 + 8), pick(w1, o1, j0 + 9));
+#pragma unroll
+            for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(smem_u32(sTab + (64 + kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                mma_bf16_16816(dq[2 * dpi], af, b0, b1);
+                mma_bf16_16816(dq[2 * dpi + 1], af, b2, b3);
+            }
+        }
+    }
+    // ---- store dQ, staged behind the tables in the K/V buffer
+    __nv_bfloat16* sO = sTab + 192 * HDP + warp * 16 * HDP;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        *reinterpret_cast<uint32_t*>(sO + g * HDP + i * 8 + 2 * t) = pack_bf16(dq[i][0], dq[i][1]);
+        *reinterpret_cast<uint32_t*>(sO + (g + 8) * HDP + i * 8 + 2 * t) = pack_bf16(dq[i][2], dq[i][3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i - r * CH;
+        *reinterpret_cast<uint4*>(p.dqkv + (tok_base + qt * 64 + warp * 16 + r) * ld + head * HD + c * 8) =
+            *reinterpret_cast<const uint4*>(sO + r * HDP + c * 8);
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64_kernel(const BwdParams p) {
+    using Plan = Bwd64Smem<HD>;
+    constexpr int HDP = Plan::HDP, KSTEPS = HD / 16, DT = HD / 8, CH = HD / 8;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dkv_off_kv);
+    __nv_bfloat16* sV = sK + BW_T * HDP;
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dkv_off_qo);
+    __nv_bfloat16* sdO = sQ + BW_T * HDP;
+    __nv_bfloat16* sRw = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dkv_off_rw);
+    __nv_bfloat16* sRh = reinterpret_cast<__nv_bfloat16*>(smem + Plan::dkv_off_rh);
+    float* sTw = reinterpret_cast<float*>(smem + Plan::dkv_off_tw);
+    float* sThc = reinterpret_cast<float*>(smem + Plan::dkv_off_row);
+    float* sLse = sThc + BW_T;
+    float* sD = sLse + BW_T;
+    constexpr int TWS = 129;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int kt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const long long tok_base = static_cast<long long>(b) * 4096;
+    const int ld = 3 * p.D;
+    const __nv_bfloat16* qbase = p.qkv + head * HD;
+    const __nv_bfloat16* kbase = qbase + p.D;
+    const __nv_bfloat16* vbase = qbase + 2 * p.D;
+
+    for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const long long row = (tok_base + kt * 64 + r) * ld + c * 8;
+        cp_async_16(smem_u32(sK + r * HDP + c * 8), kbase + row, true);
+        cp_async_16(smem_u32(sV + r * HDP + c * 8), vbase + row, true);
+    }
+    for (int i = tid; i < 128 * CH; i += BW_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        cp_async_16(smem_u32(sRw + r * HDP + c * 8), p.relw + (r < 127 ? r : 0) * HD + c * 8, r < 127);
+    }
+    for (int i = tid; i < 8 * CH; i += BW_THREADS)                 // rows 8..15 of the rel_pos_h slot stay zero
+        *reinterpret_cast<uint4*>(sRh + (8 + i / CH) * HDP + (i % CH) * 8) = make_uint4(0, 0, 0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t kf[KSTEPS][4], vf[KSTEPS][4];
+    {
+        const int row = warp * 16 + (lane & 15);
+        const int koff = (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            ldmatrix_x4(smem_u32(sK + row * HDP + ks * 16 + koff), kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3]);
+            ldmatrix_x4(smem_u32(sV + row * HDP + ks * 16 + koff), vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3]);
+        }
+    }
+    const int kx0 = warp * 16 + g, kx1 = kx0 + 8;               // this thread's two key rows = kx
+    float dk[DT][4], dv[DT][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    const int krow = (lane & 7) + ((lane >> 4) << 3);
+    const int kcol = ((lane >> 3) & 1) * 8;
+
+    for (int qt = 0; qt < 64; ++qt) {
+        __syncthreads();                                   // previous query tile fully consumed
+        for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+            const int r = i / CH, c = i - r * CH;
+            const long long tok = tok_base + qt * 64 + r;
+            cp_async_16(smem_u32(sQ + r * HDP + c * 8), qbase + tok * ld + c * 8, true);
+            cp_async_16(smem_u32(sdO + r * HDP + c * 8), p.dout + tok * p.D + head * HD + c * 8, true);
+        }
+        {   // the ONE rel_pos_h row this tile pair needs: qy - ky + 63 (rows 1..7 of the slot: the following table rows, unused)
+            const int j0 = qt - kt + 63;
+            for (int i = tid; i < 8 * CH; i += BW_THREADS) {
+                const int r = i / CH, c = i - r * CH;
+                cp_async_16(smem_u32(sRh + r * HDP + c * 8), p.relh + (j0 + r < 127 ? j0 + r : 0) * HD + c * 8, j0 + r < 127);
+            }
+        }
+        if (tid < BW_T) {
+            const long long tok = tok_base + qt * 64 + tid;
+            sLse[tid] = p.lse[tok * p.heads + head];
+            sD[tid] = p.dsum[tok * p.heads + head];
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        {   // T_w of this query tile (each warp projects 16 query rows on all 127 table rows) + the one T_h column
+            uint32_t qf[KSTEPS][4];
+            const int row = warp * 16 + (lane & 15);
+            const int koff = (lane >> 4) * 8;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks)
+                ldmatrix_x4(smem_u32(sQ + row * HDP + ks * 16 + koff), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            for (int n0 = 0; n0 < 128; n0 += 16) {
+                float acc[2][4] = {};
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(smem_u32(sRw + (n0 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                    mma_bf16_16816(acc[0], qf[ks], b0, b1);
+                    mma_bf16_16816(acc[1], qf[ks], b2, b3);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = n0 + h * 8 + 2 * t, r0 = warp * 16 + g;
+                    sTw[r0 * TWS + col] = acc[h][0] * kLog2eB;
+                    sTw[r0 * TWS + col + 1] = acc[h][1] * kLog2eB;
+                    sTw[(r0 + 8) * TWS + col] = acc[h][2] * kLog2eB;
+                    sTw[(r0 + 8) * TWS + col + 1] = acc[h][3] * kLog2eB;
+                }
+            }
+            float acc[4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sRh + krow * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(acc, qf[ks], b0, b1);
+            }
+            if (t == 0) {                                  // column 0 of the n-tile = table row qy - ky + 63
+                sThc[warp * 16 + g] = acc[0] * kLog2eB;
+                sThc[warp * 16 + g + 8] = acc[2] * kLog2eB;
+            }
+        }
+        __syncthreads();
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sQ + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(s[2 * np], kf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], kf[ks], b2, b3);
+                ldmatrix_x4(smem_u32(sdO + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(dp[2 * np], vf[ks], b0, b1);
+                mma_bf16_16816(dp[2 * np + 1], vf[ks], b2, b3);
+            }
+        }
+        uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float pv[4], dsv[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = nt * 8 + 2 * t + e;             // query column = qx
+                const float lse = sLse[q], dd = sD[q], thc = sThc[q];
+                const float* tw = sTw + q * TWS + q + 63;
+                const float l0 = fmaf(s[nt][e], p.scale_log2, thc + tw[-kx0]);
+                const float l1 = fmaf(s[nt][2 + e], p.scale_log2, thc + tw[-kx1]);
+                pv[e] = ex2f(l0 - lse);
+                pv[2 + e] = ex2f(l1 - lse);
+                dsv[e] = pv[e] * (dp[nt][e] - dd);
+                dsv[2 + e] = pv[2 + e] * (dp[nt][2 + e] - dd);
+            }
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+            dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(dsv[0], dsv[1]);
+            dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+        }
+        {
+            const int vrow = lane & 15;
+            const int vcol = (lane >> 4) * 8;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(smem_u32(sdO + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dv[2 * dpi], pf[kk], b0, b1);
+                    mma_bf16_16816(dv[2 * dpi + 1], pf[kk], b2, b3);
+                    ldmatrix_x4_trans(smem_u32(sQ + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dk[2 * dpi], dsf[kk], b0, b1);
+                    mma_bf16_16816(dk[2 * dpi + 1], dsf[kk], b2, b3);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16* oK = sK + warp * 16 * HDP;
+    __nv_bfloat16* oV = sV + warp * 16 * HDP;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        *reinterpret_cast<uint32_t*>(oK + g * HDP + i * 8 + 2 * t) = pack_bf16(dk[i][0] * p.scale, dk[i][1] * p.scale);
+        *reinterpret_cast<uint32_t*>(oK + (g + 8) * HDP + i * 8 + 2 * t) = pack_bf16(dk[i][2] * p.scale, dk[i][3] * p.scale);
+        *reinterpret_cast<uint32_t*>(oV + g * HDP + i * 8 + 2 * t) = pack_bf16(dv[i][0], dv[i][1]);
+        *reinterpret_cast<uint32_t*>(oV + (g + 8) * HDP + i * 8 + 2 * t) = pack_bf16(dv[i][2], dv[i][3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i - r * CH;
+        __nv_bfloat16* dst = p.dqkv + (tok_base + kt * 64 + warp * 16 + r) * ld + head * HD + c * 8;
+        *reinterpret_cast<uint4*>(dst + p.D) = *reinterpret_cast<const uint4*>(oK + r * HDP + c * 8);
+        *reinterpret_cast<uint4*>(dst + 2 * p.D) = *reinterpret_cast<const uint4*>(oV + r * HDP + c * 8);
+    }
+}
+
 template <int HD>
 int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
+    if (p.S == 64 && p.G == 64 && HD >= 64 && option(OPT_ATTN_LEGACY) == 0) {   // the 64 x 64 global blocks: specialised kernels
+        static unsigned char g0[kMaxDevices] = {}, g1[kMaxDevices] = {};
+        dim3 grid64(64, p.heads, batch);
+        CVLM_TRY(ensure_dynamic_smem(attn_bwd_dq64_kernel<HD>, Bwd64Smem<HD>::dq_total, g0));
+        attn_bwd_dq64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dq_total, stream>>>(p);
+        CVLM_CUDA(cudaGetLastError());
+        CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64_kernel<HD>, Bwd64Smem<HD>::dkv_total, g1));
+        attn_bwd_dkv64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dkv_total, stream>>>(p);
+        CVLM_CUDA(cudaGetLastError());
+        return CVLM_OK;
+    }
     const BwdSmem<HD> plan(p.TWP, p.TWK);
     if (plan.total > 227 * 1024) return set_error(CVLM_ERR_UNSUPPORTED, "attention_backward: shared memory %d", plan.total);
     const int L = p.S * p.S;

@@ -74,7 +74,9 @@ layernorm_train_kernel(const float* __restrict__ x, const float* __restrict__ ga
 
 // XH: where the normalised input comes from -- 0: raw bf16 x + (rstd, -mean*rstd) rows (norm1 fold), 1: saved bf16
 // xhat + rstd per row (norm2), 2: fp32 x, statistics recomputed here (neck LayerNorm2d)
-template <int XH>
+// NV > 0: cols == NV * 128 exactly (fully unrolled, no guards: the generic version keeps 2 x 16 float4 slots live and ran at
+// a third of the copy bandwidth); NV == 0: any width that is a multiple of 4
+template <int XH, int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, const void* __restrict__ xsrc,
               const float* __restrict__ stat, const float* residual, float* dx, __nv_bfloat16* __restrict__ dxb,
@@ -83,7 +85,8 @@ ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, c
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int nvec = cols >> 2;
-    float4 gv[LNB_VMAX], xh[LNB_VMAX];
+    constexpr int SLOTS = NV > 0 ? NV : LNB_VMAX;
+    float4 gv[SLOTS], xh[SLOTS];
     float rstd = 0.f, nm = 0.f;
     if (XH == 0) {
         const float2 rn = __ldg(reinterpret_cast<const float2*>(stat) + row);
@@ -97,9 +100,9 @@ ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, c
         const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(xsrc) + row * cols);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_VMAX; ++i) {
+        for (int i = 0; i < SLOTS; ++i) {
             const int idx = lane + i * 32;
-            if (idx < nvec) {
+            if (NV > 0 || idx < nvec) {
                 xh[i] = __ldcs(xr + idx);
                 s += (xh[i].x + xh[i].y) + (xh[i].z + xh[i].w);
             }
@@ -107,24 +110,24 @@ ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, c
         const float mean = warp_sum_b(s) / cols;
         float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_VMAX; ++i) {
+        for (int i = 0; i < SLOTS; ++i) {
             const int idx = lane + i * 32;
-            if (idx < nvec) {
+            if (NV > 0 || idx < nvec) {
                 xh[i].x -= mean; xh[i].y -= mean; xh[i].z -= mean; xh[i].w -= mean;
                 q += (xh[i].x * xh[i].x + xh[i].y * xh[i].y) + (xh[i].z * xh[i].z + xh[i].w * xh[i].w);
             }
         }
         rstd = 1.0f / sqrtf(warp_sum_b(q) / cols + eps);
 #pragma unroll
-        for (int i = 0; i < LNB_VMAX; ++i) {
+        for (int i = 0; i < SLOTS; ++i) {
             xh[i].x *= rstd; xh[i].y *= rstd; xh[i].z *= rstd; xh[i].w *= rstd;
         }
     } else {
         const uint2* xr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xsrc) + row * cols);
 #pragma unroll
-        for (int i = 0; i < LNB_VMAX; ++i) {
+        for (int i = 0; i < SLOTS; ++i) {
             const int idx = lane + i * 32;
-            if (idx < nvec) {
+            if (NV > 0 || idx < nvec) {
                 const uint2 pk = __ldcs(xr + idx);
                 float4 h = make_float4(__uint_as_float(pk.x << 16), __uint_as_float(pk.x & 0xffff0000u),
                                        __uint_as_float(pk.y << 16), __uint_as_float(pk.y & 0xffff0000u));
@@ -139,9 +142,9 @@ ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, c
     const float4* gr = reinterpret_cast<const float4*>(g_in + row * cols);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LNB_VMAX; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
         const int idx = lane + i * 32;
-        if (idx < nvec) {
+        if (NV > 0 || idx < nvec) {
             float4 g = __ldcs(gr + idx);
             if (gamma != nullptr) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
@@ -154,9 +157,9 @@ ln_bwd_kernel(const float* __restrict__ g_in, const float* __restrict__ gamma, c
     }
     const float m1 = warp_sum_b(s1) / cols, m2 = warp_sum_b(s2) / cols;
 #pragma unroll
-    for (int i = 0; i < LNB_VMAX; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
         const int idx = lane + i * 32;
-        if (idx < nvec) {
+        if (NV > 0 || idx < nvec) {
             float4 d;
             d.x = rstd * (gv[i].x - m1 - xh[i].x * m2);
             d.y = rstd * (gv[i].y - m1 - xh[i].y * m2);
@@ -361,10 +364,21 @@ int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void*
     const int wpb = 8;
     const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
     __nv_bfloat16* db = static_cast<__nv_bfloat16*>(dxb);
-    if (xhat_kind == 0) ln_bwd_kernel<0><<<grid, wpb * 32, 0, stream>>>(g, gamma, xsrc, stat, residual, dx, db, rows, cols, eps);
-    else if (xhat_kind == 1) ln_bwd_kernel<1><<<grid, wpb * 32, 0, stream>>>(g, gamma, xsrc, stat, residual, dx, db, rows, cols, eps);
-    else if (xhat_kind == 2) ln_bwd_kernel<2><<<grid, wpb * 32, 0, stream>>>(g, gamma, xsrc, stat, residual, dx, db, rows, cols, eps);
+#define CVLM_LNB(XH, NV) ln_bwd_kernel<XH, NV><<<grid, wpb * 32, 0, stream>>>(g, gamma, xsrc, stat, residual, dx, db, rows, cols, eps)
+#define CVLM_LNB_W(XH)                                  \
+    switch (cols) {                                     \
+        case 256: CVLM_LNB(XH, 2); break;               \
+        case 768: CVLM_LNB(XH, 6); break;               \
+        case 1024: CVLM_LNB(XH, 8); break;              \
+        case 1280: CVLM_LNB(XH, 10); break;             \
+        default: CVLM_LNB(XH, 0); break;                \
+    }
+    if (xhat_kind == 0) { CVLM_LNB_W(0) }
+    else if (xhat_kind == 1) { CVLM_LNB_W(1) }
+    else if (xhat_kind == 2) { CVLM_LNB_W(2) }
     else return set_error(CVLM_ERR_ARG, "ln_bwd: xhat_kind %d", xhat_kind);
+#undef CVLM_LNB_W
+#undef CVLM_LNB
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }

@@ -67,6 +67,21 @@ def attention_reference(qkv, relh, relw, batch, grid, window, heads, hd):
     (1, 64, 0, 1, 64),
 ])
 def test_attention_backward_matches_autograd(batch, grid, window, heads, hd):
+    _attention_backward_case(batch, grid, window, heads, hd)
+
+
+def test_attention_backward_generic_kernels_on_the_global_grid():
+    """The 64x64 global blocks normally take the specialised kernels (attn_bwd_dq64 / dkv64); the generic pair must give
+    the same gradients there ("attn_legacy" forces it, and the mma.sync forward with it)."""
+    from camouflaged_vlm_b200 import _lib
+    _lib.set_option("attn_legacy", 1)
+    try:
+        _attention_backward_case(1, 64, 0, 1, 80)
+    finally:
+        _lib.set_option("attn_legacy", 0)
+
+
+def _attention_backward_case(batch, grid, window, heads, hd):
     D = heads * hd
     S = window if window > 0 else grid
     rows = batch * grid * grid
