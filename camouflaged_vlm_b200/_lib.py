@@ -78,6 +78,8 @@ _SIGS = {
                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_longlong, C.c_void_p]),
     "cvlm_encoder_forward_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cvlm_encoder_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cvlm_encoder_last_launch_count": (C.c_longlong, [C.c_void_p]),
     "cvlm_encoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "cvlm_encoder_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -474,6 +474,7 @@ int cvlm_encoder_destroy(cvlm_encoder* enc) {
             cudaEventDestroy(sp.stop);
         }
         for (cudaEvent_t e : enc->event_pool) cudaEventDestroy(e);
+        for (cudaEvent_t e : enc->host_events) cudaEventDestroy(e);
     }
     delete enc;
     return CVLM_OK;
@@ -503,6 +504,65 @@ int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const f
     if (!x_out) return set_error(CVLM_ERR_ARG, "forward_partial: null x_out");
     return forward_impl(enc, images, highpass, batch, nullptr, nullptr, stop_after_block, x_out, workspace,
                         workspace_bytes, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer entry point: what a caller with a batch in (pinned) host memory runs.  The batch is cut into chunks; the
+// host -> device copy of chunk i+1 and the device -> host copy of the embeddings of chunk i-1 run on `copy_stream`
+// underneath the encoder of chunk i on `stream` (two device staging buffers).  Only stream-ordered waits, no host sync.
+int cvlm_encoder_forward_host(cvlm_encoder* enc, const float* images_host, int batch, int chunk, float* out_host,
+                              float* emb_dev, float* const* interm_dev, float* stage_dev, void* workspace,
+                              long long workspace_bytes, cvlm_stream_t copy_stream_, cvlm_stream_t stream_) {
+    if (!enc || !images_host || !out_host || !emb_dev || !stage_dev || !workspace)
+        return set_error(CVLM_ERR_ARG, "forward_host: null argument");
+    if (batch <= 0 || chunk <= 0) return set_error(CVLM_ERR_ARG, "forward_host: batch and chunk must be positive");
+    cudaStream_t cs = static_cast<cudaStream_t>(copy_stream_), main = static_cast<cudaStream_t>(stream_);
+    if (cs == main) return set_error(CVLM_ERR_ARG, "forward_host: the copy stream must differ from the compute stream");
+    const cvlm_encoder_config& c = enc->cfg;
+    const long long g = c.img_size / c.patch_size, T = g * g;
+    const long long img_elems = static_cast<long long>(c.in_chans) * c.img_size * c.img_size;
+    const long long emb_elems = static_cast<long long>(c.out_chans) * T;
+    int n_glob = 0;
+    for (int i = 0; i < c.depth; ++i) n_glob += c.is_global[i] ? 1 : 0;
+    while (enc->host_events.size() < 5) {
+        cudaEvent_t e = nullptr;
+        CVLM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        enc->host_events.push_back(e);
+    }
+    cudaEvent_t ready[2] = {enc->host_events[0], enc->host_events[1]}, freed[2] = {enc->host_events[2], enc->host_events[3]};
+    cudaEvent_t edge = enc->host_events[4];
+    CVLM_CUDA(cudaEventRecord(edge, main));                 // the copy stream starts after what is already queued
+    CVLM_CUDA(cudaStreamWaitEvent(cs, edge, 0));
+    const int n_chunks = (batch + chunk - 1) / chunk;
+    auto upload = [&](int i) -> int {
+        const int s = i * chunk, e = s + chunk < batch ? s + chunk : batch;
+        if (i >= 2) CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));
+        CVLM_CUDA(cudaMemcpyAsync(stage_dev + static_cast<long long>(i & 1) * chunk * img_elems, images_host + s * img_elems,
+                                  static_cast<size_t>(e - s) * img_elems * 4, cudaMemcpyHostToDevice, cs));
+        CVLM_CUDA(cudaEventRecord(ready[i & 1], cs));
+        return CVLM_OK;
+    };
+    CVLM_TRY(upload(0));
+    long long launches = 0;
+    std::vector<float*> islice(static_cast<size_t>(n_glob > 0 ? n_glob : 1), nullptr);
+    for (int i = 0; i < n_chunks; ++i) {
+        const int s = i * chunk, e = s + chunk < batch ? s + chunk : batch;
+        if (i + 1 < n_chunks) CVLM_TRY(upload(i + 1));
+        CVLM_CUDA(cudaStreamWaitEvent(main, ready[i & 1], 0));
+        if (interm_dev)
+            for (int k = 0; k < n_glob; ++k) islice[k] = interm_dev[k] + static_cast<long long>(s) * T * c.embed_dim;
+        CVLM_TRY(forward_impl(enc, stage_dev + static_cast<long long>(i & 1) * chunk * img_elems, nullptr, e - s,
+                              emb_dev + s * emb_elems, interm_dev ? islice.data() : nullptr, -1, nullptr, workspace,
+                              workspace_bytes, nullptr, 0, main));
+        launches += enc->last_launches;
+        CVLM_CUDA(cudaEventRecord(freed[i & 1], main));
+        CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));      // this chunk's embeddings leave under the next chunk's encoder
+        CVLM_CUDA(cudaMemcpyAsync(out_host + s * emb_elems, emb_dev + s * emb_elems, static_cast<size_t>(e - s) * emb_elems * 4,
+                                  cudaMemcpyDeviceToHost, cs));
+    }
+    CVLM_CUDA(cudaEventRecord(edge, cs));
+    CVLM_CUDA(cudaStreamWaitEvent(main, edge, 0));          // out_host is valid once `stream` has been synchronised
+    enc->last_launches = launches;
+    return CVLM_OK;
 }
 
 long long cvlm_encoder_last_launch_count(const cvlm_encoder* enc) { return enc ? enc->last_launches : 0; }

@@ -27,6 +27,7 @@ struct cvlm_encoder {
     bool profiling = false;
     std::vector<ProfSpan> spans;        // spans of the profiled forwards since the last get_profile
     std::vector<cudaEvent_t> event_pool;
+    std::vector<cudaEvent_t> host_events;   // cvlm_encoder_forward_host: staging-buffer ready / consumed, stream edges
 };
 
 namespace cvlm {

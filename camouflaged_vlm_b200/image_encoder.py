@@ -381,9 +381,9 @@ class ImageEncoderViT(nn.Module):
         n_glob = sum(1 for i in range(cfg.depth) if cfg.block_window(i) == 0)
         interms = [torch.empty(B, g, g, cfg.embed_dim, device=dev, dtype=torch.float32) for _ in range(n_glob)] if interm else []
         shape = (min(chunk, B),) + tuple(x_host.shape[1:])
-        if getattr(self, "_stage", None) is None or self._stage[0].shape != shape or self._stage[0].device != dev:
-            self._stage = [torch.empty(shape, device=dev, dtype=torch.float32) for _ in range(2)]
-        stage = self._stage
+        if getattr(self, "_stage", None) is None or tuple(self._stage.shape[1:]) != shape or self._stage.device != dev:
+            self._stage = torch.empty((2,) + shape, device=dev, dtype=torch.float32)     # two staging buffers, back to back
+        stage = [self._stage[0], self._stage[1]]
         ready = [torch.cuda.Event() for _ in range(2)]        # staging buffer filled
         free = [torch.cuda.Event() for _ in range(2)]         # staging buffer consumed by the encoder
         spans = [(s, min(B, s + chunk)) for s in range(0, B, chunk)]
@@ -399,6 +399,26 @@ class ImageEncoderViT(nn.Module):
 
         if out_host is None:
             out_host = torch.empty(B, cfg.out_chans, g, g, dtype=torch.float32, pin_memory=True)
+        if on_chunk is None and x_host.dtype == torch.float32 and x_host.is_contiguous() and out_host.is_contiguous():
+            # the whole pipeline in ONE C-ABI call (cvlm_encoder_forward_host): same copies, same stream choreography
+            self._ensure_ready(dev)
+            lib = _lib.load()
+            ws = self._get_workspace(min(chunk, B), dev)
+            iptr = None
+            if interms:
+                arr = (C.c_void_p * len(interms))(*[t.data_ptr() for t in interms])
+                iptr = C.cast(arr, C.POINTER(C.c_void_p))
+            with torch.cuda.device(dev):
+                _lib.check(lib.cvlm_encoder_forward_host(self._handle, x_host.data_ptr(), B, min(chunk, B), out_host.data_ptr(),
+                                                         emb.data_ptr(), iptr, stage[0].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                         cs.cuda_stream, main.cuda_stream), "cvlm_encoder_forward_host")
+            self.last_launch_count = lib.cvlm_encoder_last_launch_count(self._handle)
+            ret = [out_host]     # (x_host must stay alive until the stream has run, as with any asynchronous copy)
+            if return_device:
+                ret.append(emb)
+            if interm:
+                ret.append([t.permute(0, 3, 1, 2) for t in interms])
+            return ret[0] if len(ret) == 1 else tuple(ret)
         upload(0)
         for i, (s, e) in enumerate(spans):
             if i + 1 < len(spans):

@@ -106,6 +106,17 @@ int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const f
 
 /* Number of kernel launches the last cvlm_encoder_forward on this handle issued (for bench.py's
  * gpu_launches claim). */
+/* The same forward for a batch that lives in HOST memory (the reference-facing call of a serving loop: images arrive on
+ * the host, the decoder / caller wants the embeddings back; replaces `self.image_encoder(input.to(device), ...)`,
+ * models/sam_maskdecoder_edge.py:203-208, 337).  images_host fp32 [batch,3,S,S] and out_host fp32 [batch,out,g,g] should be
+ * pinned.  The batch is cut into chunks of `chunk` images: the upload of chunk i+1 and the download of the embeddings of
+ * chunk i-1 run on `copy_stream` underneath the encoder of chunk i on `stream` (stage_dev: device, 2*chunk*3*S*S floats;
+ * emb_dev: device, [batch,out,g,g]; interm_dev: NULL or one device pointer [batch,g,g,D] per global block; workspace for
+ * `chunk` images).  Stream-ordered only: out_host is valid once `stream` has been synchronised. */
+int cvlm_encoder_forward_host(cvlm_encoder* enc, const float* images_host, int batch, int chunk, float* out_host,
+                              float* emb_dev, float* const* interm_dev, float* stage_dev, void* workspace,
+                              long long workspace_bytes, cvlm_stream_t copy_stream, cvlm_stream_t stream);
+
 long long cvlm_encoder_last_launch_count(const cvlm_encoder* enc);
 
 /* Per-kernel timing.  With profiling enabled every launch of cvlm_encoder_forward is bracketed by CUDA

@@ -31,7 +31,7 @@ def main():
             continue
         if cur is None:
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P[T\d]+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m:
             kernels[cur]["_total"] += 1
             op = m.group(1)
