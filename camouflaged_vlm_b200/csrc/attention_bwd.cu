@@ -1257,6 +1257,405 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64_kernel(const Bwd
     }
 }
 
+// ================================================================================================
+// 14 x 14 windows: one CTA per (window, head) with everything resident.  The generic pair above cuts the 196 tokens of
+// a window into 4 x 4 tiles of 64 (the fourth holds 4 rows) and launches 25 600 small CTAs per block, each a chain of
+// load -> sync -> mma steps: measured 2.25 ms per block for 8 images against 0.14 ms for the forward.  Here 13 warps own
+// 16 rows each of the 208-row (196 + padding) Q, K, V, dO tiles in shared memory:
+//   phase A1  (rows = queries)  T = q . rel_pos for the warp's rows, row log-sum-exp (online over 13 key steps)
+//   phase B   (rows = keys)     per 16-query step: S^T and dP^T blocks -> P^T, dS^T fragments -> dV += P^T dO, dK += dS^T Q
+//   phase A2  (rows = queries)  per 16-key step: S and dP blocks -> dS fragment -> dQ += dS K, dSh / dSw (indicator products);
+//                               then dQ += dT_h R_h + dT_w R_w
+// No fragment array is ever held for a whole row: every 16 x 16 block of P / dS is consumed as the k-step it is.
+constexpr int WB_S = 14, WB_L = 196, WB_LP = 208, WB_WARPS = 13, WB_THREADS = WB_WARPS * 32, WB_TS = 33;
+template <int HD>
+struct WinBwdSmem {
+    static constexpr int HDP = HD + 8;
+    static constexpr int TILE = WB_LP * HDP * 2;
+    static constexpr int off_q = 0, off_k = TILE, off_v = 2 * TILE, off_do = 3 * TILE, off_rel = 4 * TILE;
+    static constexpr int off_th = off_rel + 2 * 32 * HDP * 2, off_tw = off_th + WB_LP * WB_TS * 4;
+    static constexpr int off_lse = off_tw + WB_LP * WB_TS * 4, off_d = off_lse + WB_LP * 4, off_yx = off_d + WB_LP * 4;
+    static constexpr int off_gt = off_yx + WB_LP * 4, total = off_gt + WB_LP * 4;
+    static_assert(total <= 227 * 1024, "window backward shared memory");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(WB_THREADS, 1) attn_bwd_win14_kernel(const BwdParams p) {
+    using Plan = WinBwdSmem<HD>;
+    constexpr int HDP = Plan::HDP, KSTEPS = HD / 16, DT = HD / 8, CH = HD / 8, NP = WB_LP / 16;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem + Plan::off_q);
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + Plan::off_k);
+    __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(smem + Plan::off_v);
+    __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(smem + Plan::off_do);
+    __nv_bfloat16* sRel = reinterpret_cast<__nv_bfloat16*>(smem + Plan::off_rel);     // [0,32): rel_pos_h, [32,64): rel_pos_w
+    float* sTh = reinterpret_cast<float*>(smem + Plan::off_th);
+    float* sTw = reinterpret_cast<float*>(smem + Plan::off_tw);
+    float* sLse = reinterpret_cast<float*>(smem + Plan::off_lse);
+    float* sD = reinterpret_cast<float*>(smem + Plan::off_d);
+    short2* sYx = reinterpret_cast<short2*>(smem + Plan::off_yx);
+    int* sGt = reinterpret_cast<int*>(smem + Plan::off_gt);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.x, bw = blockIdx.y;
+    const int G = p.G, win = bw % (p.nW * p.nW);
+    const int wy = win / p.nW, wx = win % p.nW;
+    const long long tok_base = static_cast<long long>(bw / (p.nW * p.nW)) * G * G;
+    const int ld = 3 * p.D;
+    const __nv_bfloat16* qbase = p.qkv + head * HD;
+
+    // ---- phase 0: the window's Q, K, V, dO rows (zero for padding), tables, D = rowsum(dO * o)
+    for (int r = tid; r < WB_LP; r += WB_THREADS) {
+        int ly = 0, lx = 0, gt = -1;
+        if (r < WB_L) {
+            ly = r / WB_S;
+            lx = r - ly * WB_S;
+            const int gy = wy * WB_S + ly, gx = wx * WB_S + lx;
+            if (gy < G && gx < G) gt = gy * G + gx;
+        }
+        sYx[r] = make_short2(static_cast<short>(ly), static_cast<short>(lx));
+        sGt[r] = gt;
+    }
+    for (int i = tid; i < WB_LP * CH; i += WB_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        int gt = -1;
+        if (r < WB_L) {
+            const int ly = r / WB_S, lx = r - ly * WB_S;
+            const int gy = wy * WB_S + ly, gx = wx * WB_S + lx;
+            if (gy < G && gx < G) gt = gy * G + gx;
+        }
+        const long long tok = tok_base + (gt < 0 ? 0 : gt);
+        const __nv_bfloat16* src = qbase + tok * ld + c * 8;
+        cp_async_16(smem_u32(sQ + r * HDP + c * 8), src, gt >= 0);
+        cp_async_16(smem_u32(sK + r * HDP + c * 8), src + p.D, gt >= 0);
+        cp_async_16(smem_u32(sV + r * HDP + c * 8), src + 2 * p.D, gt >= 0);
+        cp_async_16(smem_u32(sdO + r * HDP + c * 8), p.dout + tok * p.D + head * HD + c * 8, gt >= 0);
+    }
+    for (int i = tid; i < 64 * CH; i += WB_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const bool is_w = r >= 32;
+        const int row = is_w ? r - 32 : r;
+        const __nv_bfloat16* tab = is_w ? p.relw : p.relh;
+        cp_async_16(smem_u32(sRel + r * HDP + c * 8), tab + (row < 27 ? row : 0) * HD + c * 8, row < 27);
+    }
+    cp_async_commit();
+    {
+        const int r = tid >> 1, half = tid & 1;                   // 416 threads = 2 per row
+        int gt = -1;
+        if (r < WB_L) {
+            const int ly = r / WB_S, lx = r - ly * WB_S;
+            const int gy = wy * WB_S + ly, gx = wx * WB_S + lx;
+            if (gy < G && gx < G) gt = gy * G + gx;
+        }
+        float d = 0.f;
+        if (gt >= 0) {
+            const __nv_bfloat16* po = p.o + (tok_base + gt) * p.D + head * HD + half * (HD / 2);
+            const __nv_bfloat16* pd = p.dout + (tok_base + gt) * p.D + head * HD + half * (HD / 2);
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+                const uint4 a = *reinterpret_cast<const uint4*>(po + c * 8), b = *reinterpret_cast<const uint4*>(pd + c * 8);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    d = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(bw4[e] << 16), d);
+                    d = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(bw4[e] & 0xffff0000u), d);
+                }
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        if (half == 0) sD[r] = d;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int krow = (lane & 7) + ((lane >> 4) << 3);
+    const int kcol = ((lane >> 3) & 1) * 8;
+    const int vrow = lane & 15;
+    const int vcol = (lane >> 4) * 8;
+    const int arow = warp * 16 + (lane & 15);
+    const int akoff = (lane >> 4) * 8;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    const short2 yx0 = sYx[r0], yx1 = sYx[r1];
+
+    // ---- phase A1: T rows and the row log-sum-exp of this warp's 16 queries
+    uint32_t qf[KSTEPS][4];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+        ldmatrix_x4(smem_u32(sQ + arow * HDP + ks * 16 + akoff), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    for (int which = 0; which < 2; ++which) {
+        const __nv_bfloat16* sR = sRel + which * 32 * HDP;
+        float* sT = which ? sTw : sTh;
+#pragma unroll
+        for (int n0 = 0; n0 < 32; n0 += 16) {
+            float acc[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sR + (n0 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(acc[0], qf[ks], b0, b1);
+                mma_bf16_16816(acc[1], qf[ks], b2, b3);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = n0 + h * 8 + 2 * t;
+                sT[r0 * WB_TS + col] = acc[h][0] * kLog2eB;
+                sT[r0 * WB_TS + col + 1] = acc[h][1] * kLog2eB;
+                sT[r1 * WB_TS + col] = acc[h][2] * kLog2eB;
+                sT[r1 * WB_TS + col + 1] = acc[h][3] * kLog2eB;
+            }
+        }
+    }
+    __syncwarp();
+    const float* th0 = sTh + r0 * WB_TS + yx0.x + 13;
+    const float* th1 = sTh + r1 * WB_TS + yx1.x + 13;
+    const float* tw0 = sTw + r0 * WB_TS + yx0.y + 13;
+    const float* tw1 = sTw + r1 * WB_TS + yx1.y + 13;
+    // logits (log2 domain) of the 16-key step np for this thread's 2 rows x 4 columns; keys >= 196 -> -inf
+    auto logit_block = [&](const float (&acc)[2][4], int np, float (&l)[2][4]) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = np * 16 + h2 * 8 + 2 * t + e;
+                const short2 k = sYx[col];
+                const bool live = col < WB_L;
+                const float v0 = fmaf(acc[h2][e], p.scale_log2, th0[-k.x] + tw0[-k.y]);
+                const float v1 = fmaf(acc[h2][2 + e], p.scale_log2, th1[-k.x] + tw1[-k.y]);
+                l[h2][e] = live ? v0 : -INFINITY;
+                l[h2][2 + e] = live ? v1 : -INFINITY;
+            }
+    };
+    float lse[2];
+    {
+        float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int np = 0; np < NP; ++np) {
+            float acc[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sK + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(acc[0], qf[ks], b0, b1);
+                mma_bf16_16816(acc[1], qf[ks], b2, b3);
+            }
+            float l[2][4];
+            logit_block(acc, np, l);
+            float mx0 = fmaxf(fmaxf(l[0][0], l[0][1]), fmaxf(l[1][0], l[1][1]));
+            float mx1 = fmaxf(fmaxf(l[0][2], l[0][3]), fmaxf(l[1][2], l[1][3]));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float n0 = fmaxf(m_run[0], mx0), n1 = fmaxf(m_run[1], mx1);     // finite from the first step on
+            l_run[0] = l_run[0] * ex2f(m_run[0] - n0) + ex2f(l[0][0] - n0) + ex2f(l[0][1] - n0) + ex2f(l[1][0] - n0) + ex2f(l[1][1] - n0);
+            l_run[1] = l_run[1] * ex2f(m_run[1] - n1) + ex2f(l[0][2] - n1) + ex2f(l[0][3] - n1) + ex2f(l[1][2] - n1) + ex2f(l[1][3] - n1);
+            m_run[0] = n0;
+            m_run[1] = n1;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+            lse[h] = m_run[h] + log2f(l_run[h]);
+        }
+        if (t == 0) {
+            sLse[r0] = r0 < WB_L ? lse[0] : INFINITY;             // rows beyond the window: P = exp2(l - inf) = 0 in phase B
+            sLse[r1] = r1 < WB_L ? lse[1] : INFINITY;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: this warp's 16 KEY rows
+    {
+        uint32_t kf[KSTEPS][4], vf[KSTEPS][4];
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            ldmatrix_x4(smem_u32(sK + arow * HDP + ks * 16 + akoff), kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3]);
+            ldmatrix_x4(smem_u32(sV + arow * HDP + ks * 16 + akoff), vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3]);
+        }
+        float dk[DT][4], dv[DT][4];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+            dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+        }
+        const bool kl0 = r0 < WB_L, kl1 = r1 < WB_L;
+#pragma unroll 1
+        for (int np = 0; np < NP; ++np) {
+            float as[2][4] = {}, ap[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sQ + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(as[0], kf[ks], b0, b1);
+                mma_bf16_16816(as[1], kf[ks], b2, b3);
+                ldmatrix_x4(smem_u32(sdO + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(ap[0], vf[ks], b0, b1);
+                mma_bf16_16816(ap[1], vf[ks], b2, b3);
+            }
+            uint32_t pf[4], dsf[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                float pv[4], dsv[4];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int q = np * 16 + h2 * 8 + 2 * t + e;        // query column
+                    const short2 qy = sYx[q];
+                    const float lq = sLse[q], dd = sD[q];
+                    const float* thq = sTh + q * WB_TS + qy.x + 13;
+                    const float* twq = sTw + q * WB_TS + qy.y + 13;
+                    const float l0 = fmaf(as[h2][e], p.scale_log2, thq[-yx0.x] + twq[-yx0.y]);
+                    const float l1 = fmaf(as[h2][2 + e], p.scale_log2, thq[-yx1.x] + twq[-yx1.y]);
+                    pv[e] = kl0 ? ex2f(l0 - lq) : 0.f;
+                    pv[2 + e] = kl1 ? ex2f(l1 - lq) : 0.f;
+                    dsv[e] = pv[e] * (ap[h2][e] - dd);
+                    dsv[2 + e] = pv[2 + e] * (ap[h2][2 + e] - dd);
+                }
+                pf[h2 * 2 + 0] = pack_bf16(pv[0], pv[1]);
+                pf[h2 * 2 + 1] = pack_bf16(pv[2], pv[3]);
+                dsf[h2 * 2 + 0] = pack_bf16(dsv[0], dsv[1]);
+                dsf[h2 * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+            }
+#pragma unroll
+            for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(smem_u32(sdO + (np * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                mma_bf16_16816(dv[2 * dpi], pf, b0, b1);
+                mma_bf16_16816(dv[2 * dpi + 1], pf, b2, b3);
+                ldmatrix_x4_trans(smem_u32(sQ + (np * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                mma_bf16_16816(dk[2 * dpi], dsf, b0, b1);
+                mma_bf16_16816(dk[2 * dpi + 1], dsf, b2, b3);
+            }
+        }
+        const int gt0 = sGt[r0], gt1 = sGt[r1];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            if (gt0 >= 0) {
+                __nv_bfloat16* dst = p.dqkv + (tok_base + gt0) * ld + head * HD + i * 8 + 2 * t;
+                *reinterpret_cast<uint32_t*>(dst + p.D) = pack_bf16(dk[i][0] * p.scale, dk[i][1] * p.scale);
+                *reinterpret_cast<uint32_t*>(dst + 2 * p.D) = pack_bf16(dv[i][0], dv[i][1]);
+            }
+            if (gt1 >= 0) {
+                __nv_bfloat16* dst = p.dqkv + (tok_base + gt1) * ld + head * HD + i * 8 + 2 * t;
+                *reinterpret_cast<uint32_t*>(dst + p.D) = pack_bf16(dk[i][2] * p.scale, dk[i][3] * p.scale);
+                *reinterpret_cast<uint32_t*>(dst + 2 * p.D) = pack_bf16(dv[i][2], dv[i][3]);
+            }
+        }
+    }
+    __syncthreads();             // every warp is done with the T rows of the others: they may be overwritten below
+
+    // ---- phase A2: this warp's 16 QUERY rows again
+    {
+        uint32_t dof[KSTEPS][4];
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks)
+            ldmatrix_x4(smem_u32(sdO + arow * HDP + ks * 16 + akoff), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
+        const float d0 = sD[r0], d1 = sD[r1];
+        float dq[DT][4], ah[2][4], aw[2][4];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            ah[i][0] = ah[i][1] = ah[i][2] = ah[i][3] = 0.f;
+            aw[i][0] = aw[i][1] = aw[i][2] = aw[i][3] = 0.f;
+        }
+#pragma unroll 1
+        for (int np = 0; np < NP; ++np) {
+            float as[2][4] = {}, ap[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sK + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(as[0], qf[ks], b0, b1);
+                mma_bf16_16816(as[1], qf[ks], b2, b3);
+                ldmatrix_x4(smem_u32(sV + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(ap[0], dof[ks], b0, b1);
+                mma_bf16_16816(ap[1], dof[ks], b2, b3);
+            }
+            float l[2][4];
+            logit_block(as, np, l);
+            uint32_t dsf[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const float e0 = ex2f(l[h2][0] - lse[0]) * (ap[h2][0] - d0), e1 = ex2f(l[h2][1] - lse[0]) * (ap[h2][1] - d0);
+                const float e2 = ex2f(l[h2][2] - lse[1]) * (ap[h2][2] - d1), e3 = ex2f(l[h2][3] - lse[1]) * (ap[h2][3] - d1);
+                dsf[h2 * 2 + 0] = pack_bf16(e0, e1);
+                dsf[h2 * 2 + 1] = pack_bf16(e2, e3);
+            }
+#pragma unroll
+            for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(smem_u32(sK + (np * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                mma_bf16_16816(dq[2 * dpi], dsf, b0, b1);
+                mma_bf16_16816(dq[2 * dpi + 1], dsf, b2, b3);
+            }
+            const short2 y0 = sYx[np * 16 + 2 * t], y1 = sYx[np * 16 + 2 * t + 1];
+            const short2 y2 = sYx[np * 16 + 2 * t + 8], y3 = sYx[np * 16 + 2 * t + 9];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = j * 8 + g;
+                const uint32_t h0 = (y0.x == n ? 0x3F80u : 0u) | (y1.x == n ? 0x3F800000u : 0u);
+                const uint32_t h1 = (y2.x == n ? 0x3F80u : 0u) | (y3.x == n ? 0x3F800000u : 0u);
+                const uint32_t w0 = (y0.y == n ? 0x3F80u : 0u) | (y1.y == n ? 0x3F800000u : 0u);
+                const uint32_t w1 = (y2.y == n ? 0x3F80u : 0u) | (y3.y == n ? 0x3F800000u : 0u);
+                mma_bf16_16816(ah[j], dsf, h0, h1);
+                mma_bf16_16816(aw[j], dsf, w0, w1);
+            }
+        }
+        // (keys 196..207 have dS = 0, so their (0, 0) coordinates add nothing to dSh / dSw)
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            dq[i][0] *= p.scale; dq[i][1] *= p.scale; dq[i][2] *= p.scale; dq[i][3] *= p.scale;
+        }
+        // dSh / dSw into this warp's own (now private) T rows, then dQ += dT_h R_h + dT_w R_w with dT[q][j] = dS*[q][q* + 13 - j]
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = j * 8 + 2 * t;
+            sTh[r0 * WB_TS + col] = ah[j][0]; sTh[r0 * WB_TS + col + 1] = ah[j][1];
+            sTh[r1 * WB_TS + col] = ah[j][2]; sTh[r1 * WB_TS + col + 1] = ah[j][3];
+            sTw[r0 * WB_TS + col] = aw[j][0]; sTw[r0 * WB_TS + col + 1] = aw[j][1];
+            sTw[r1 * WB_TS + col] = aw[j][2]; sTw[r1 * WB_TS + col + 1] = aw[j][3];
+        }
+        __syncwarp();
+        for (int which = 0; which < 2; ++which) {
+            const float* row0 = (which ? sTw : sTh) + r0 * WB_TS;
+            const float* row1 = (which ? sTw : sTh) + r1 * WB_TS;
+            const __nv_bfloat16* sR = sRel + which * 32 * HDP;
+            const int o0 = (which ? yx0.y : yx0.x) + 13, o1 = (which ? yx1.y : yx1.x) + 13;
+            auto pick = [&](const float* row, int off, int j) -> float {
+                const int y = off - j;
+                return (y >= 0 && y < WB_S) ? row[y] : 0.f;
+            };
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int j0 = kk * 16 + 2 * t;
+                uint32_t af[4];
+                af[0] = pack_bf16(pick(row0, o0, j0), pick(row0, o0, j0 + 1));
+                af[1] = pack_bf16(pick(row1, o1, j0), pick(row1, o1, j0 + 1));
+                af[2] = pack_bf16(pick(row0, o0, j0 + 8), pick(row0, o0, j0 + 9));
+                af[3] = pack_bf16(pick(row1, o1, j0 + 8), pick(row1, o1, j0 + 9));
+#pragma unroll
+                for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(smem_u32(sR + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dq[2 * dpi], af, b0, b1);
+                    mma_bf16_16816(dq[2 * dpi + 1], af, b2, b3);
+                }
+            }
+        }
+        const int gt0 = sGt[r0], gt1 = sGt[r1];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            if (gt0 >= 0)
+                *reinterpret_cast<uint32_t*>(p.dqkv + (tok_base + gt0) * ld + head * HD + i * 8 + 2 * t) = pack_bf16(dq[i][0], dq[i][1]);
+            if (gt1 >= 0)
+                *reinterpret_cast<uint32_t*>(p.dqkv + (tok_base + gt1) * ld + head * HD + i * 8 + 2 * t) = pack_bf16(dq[i][2], dq[i][3]);
+        }
+    }
+}
+
 template <int HD>
 int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
     if (p.S == 64 && p.G == 64 && HD >= 64 && option(OPT_ATTN_LEGACY) == 0) {   // the 64 x 64 global blocks: specialised kernels
@@ -1267,6 +1666,14 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
         CVLM_CUDA(cudaGetLastError());
         CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64_kernel<HD>, Bwd64Smem<HD>::dkv_total, g1));
         attn_bwd_dkv64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dkv_total, stream>>>(p);
+        CVLM_CUDA(cudaGetLastError());
+        return CVLM_OK;
+    }
+    if (p.S == WB_S && HD >= 64 && option(OPT_ATTN_LEGACY) == 0) {   // 14 x 14 windows: one CTA per (window, head)
+        static unsigned char gw[kMaxDevices] = {};
+        CVLM_TRY(ensure_dynamic_smem(attn_bwd_win14_kernel<HD>, WinBwdSmem<HD>::total, gw));
+        dim3 gridw(p.heads, batch * p.nW * p.nW);
+        attn_bwd_win14_kernel<HD><<<gridw, WB_THREADS, WinBwdSmem<HD>::total, stream>>>(p);
         CVLM_CUDA(cudaGetLastError());
         return CVLM_OK;
     }
