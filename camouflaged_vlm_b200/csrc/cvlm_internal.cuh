@@ -74,6 +74,10 @@ struct GemmArgs {
     // in its epilogue.  Each partial has exactly one writer, so results do not depend on scheduling.
     void* copy_bf16 = nullptr;  long long ldc = 0;       // producer: bf16 copy of out (must not alias a1 / a2)
     float* stat_out = nullptr;  int stat_groups = 0;     // producer: fp32 [m, stat_groups, 2], stat_groups = ceil(n / CVLM_STAT_GROUP_COLS)
+    // producer, optional: fp32 [m, 2] = the (rstd, -mean * rstd) rows of the PREVIOUS LayerNorm input of the same rows.  The
+    // copy and the statistics are then taken of (x - c), c = that earlier mean: LN(x - c) == LN(x), but a row whose
+    // |mean| is large against its spread loses nothing to the bf16 rounding of the copy or to E[x^2] - mean^2.
+    const float* shift_rows = nullptr;
     const float* ln_rows = nullptr;                      // consumer: fp32 [m, 2] = (rstd, -mean * rstd) of the A rows
     const float* ln_colsum = nullptr;                    // consumer: fp32 [n]
     // Batched mode: `batch` independent products that share A1 / A2.  Entry b multiplies by the B columns

@@ -184,8 +184,10 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
         return reinterpret_cast<__nv_bfloat16*>(train ? blk_ptr(blk, sv.b_xb) : wsb + ws.off_xb);
     };
     auto rows_of = [&](int blk) { return reinterpret_cast<float*>(train ? blk_ptr(blk, sv.b_rows1) : wsb + ws.off_rows); };
-    auto feeds_norm = [&](GemmArgs& ga, int blk) {
+    // shift_blk >= 0: the rows of block `shift_blk`'s input give the per-row shift of the copy (GemmArgs::shift_rows)
+    auto feeds_norm = [&](GemmArgs& ga, int blk, int shift_blk) {
         ga.copy_bf16 = xb_of(blk); ga.ldc = D; ga.stat_out = stat; ga.stat_groups = sgroups;
+        ga.shift_rows = shift_blk >= 0 ? rows_of(shift_blk) : nullptr;
     };
     auto normed = [&](GemmArgs& ga, const void* colsum, int blk) {
         ga.ln_rows = rows_of(blk); ga.ln_colsum = static_cast<const float*>(colsum);
@@ -264,17 +266,17 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
     auto finalize_norm = [&](int blk) -> int {
         return f.run(K_LAYERNORM, [&] { return ln_finalize_launch(stat, sgroups, D, c.ln_eps, rows_of(blk), M, stream); });
     };
-    auto prompt_add = [&](int blk, const float* src, float* dst) -> int {
+    auto prompt_add = [&](int blk, const float* src, float* dst, int shift_blk) -> int {
         // dst = src + gall_blk * Wshared^T + bshared    (shared_mlp :294, add :145); dst is the next norm1 input
         GemmArgs ga;
         ga.a1 = gall + static_cast<long long>(blk) * RP; ga.lda1 = ldg; ga.b1 = sh_w; ga.ldb1 = RP; ga.k1 = RP;
         ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(sh_b);
         ga.residual = src; ga.ldr = D; ga.out = dst; ga.ldo = D;
-        feeds_norm(ga, blk);
+        feeds_norm(ga, blk, shift_blk);
         CVLM_TRY(f.gemm(K_GEMM_OTHER, ga));
         return finalize_norm(blk);
     };
-    CVLM_TRY(prompt_add(0, x, x));
+    CVLM_TRY(prompt_add(0, x, x, -1));
 
     auto finish_partial = [&](const float* src) -> int {
         CVLM_CUDA(cudaMemcpyAsync(x_out, src, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
@@ -360,14 +362,14 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
             }
             ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(fold ? l2bf : l2b);
             ga.residual = xcur; ga.ldr = D; ga.out = dst; ga.ldo = D;
-            if (fold) feeds_norm(ga, i + 1);      // otherwise prompt_add below writes the next norm1 input
+            if (fold) feeds_norm(ga, i + 1, i);   // otherwise prompt_add below writes the next norm1 input
             CVLM_TRY(f.gemm(K_GEMM_LIN2, ga));
             if (fold) CVLM_TRY(finalize_norm(i + 1));
         }
         if (want_interm) ++interm_idx;
         if (stop_here) return finish_partial(dst);
         if (!fold && !last) {
-            CVLM_TRY(prompt_add(i + 1, dst, x));
+            CVLM_TRY(prompt_add(i + 1, dst, x, i));
             xcur = x;
         } else {
             xcur = dst;

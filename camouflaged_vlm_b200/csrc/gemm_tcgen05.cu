@@ -67,6 +67,7 @@ struct GemmEpi {
                                   // 256): a narrow output does not pay for a 256-wide tile on the tensor pipe
     const __nv_bfloat16* aux;     // bf16 path, backward of a GELU layer: out = acc * gelu'(aux[row, col])
     long long ldaux;
+    const float2* shift_rows;     // producer: per-row shift c = -y / x taken from the PREVIOUS LayerNorm rows (GemmArgs::shift_rows)
 };
 
 // Exact-erf GELU (nn.GELU default, common.py:26): gelu(x) = x * Phi(x) with Phi from Abramowitz-Stegun 7.1.26
@@ -335,6 +336,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                 }
             }
             float st1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, st2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            // producer: the bf16 copy and the statistics are taken of (x - c) with c the row's mean one block earlier, so
+            // that neither the bf16 rounding nor E[x^2] - mean^2 see a large common offset of the row
+            float shc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if ((FEAT & F_PRODUCER) && !out_bf16 && ep.shift_rows != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = row_base + 4 * i + (lane >> 3);
+                    if (row < M) {
+                        const float2 rn = __ldg(ep.shift_rows + row);
+                        shc[i] = -rn.y / rn.x;
+                    }
+                }
+            }
             mbar_wait(tfull_bar(acc), (iter >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -417,6 +431,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 x.x = fabsf(x.x); x.y = fabsf(x.y); x.z = fabsf(x.z); x.w = fabsf(x.w);
                             }
                             *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (brow + row) * ep.ldo + col) = x;
+                            if (FEAT & F_PRODUCER) {
+                                const float c = shc[i];
+                                x.x -= c; x.y -= c; x.z -= c; x.w -= c;      // (out has been stored: x is dead after this)
+                            }
                             if ((FEAT & F_PRODUCER) && ep.copy_bf16 != nullptr) {
                                 uint2 pk;
                                 pk.x = pack_bf16(x.x, x.y);
@@ -740,13 +758,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         return set_error(CVLM_ERR_ARG, "gemm: the bf16 copy must not alias an A operand (other tiles still read it)");
     if (a.stat_out && a.stat_groups != (a.n + EPI_COLS - 1) / EPI_COLS)
         return set_error(CVLM_ERR_ARG, "gemm: stat_groups must be ceil(n / %d)", EPI_COLS);
+    if (a.shift_rows && (a.out_bf16 || !a.copy_bf16 || (reinterpret_cast<uintptr_t>(a.shift_rows) & 7)))
+        return set_error(CVLM_ERR_ARG, "gemm: shift_rows belongs to the fp32 producer epilogue (bf16 copy + statistics)");
     if (a.ln_rows && (!a.out_bf16 || !a.ln_colsum || (reinterpret_cast<uintptr_t>(a.ln_colsum) & 15) ||
                       (reinterpret_cast<uintptr_t>(a.ln_rows) & 7)))
         return set_error(CVLM_ERR_ARG, "gemm: the LayerNorm epilogue needs bf16 output, column sums and finalized row statistics");
     GemmEpi ep{a.bias, a.residual, a.ldr, a.res_row_mod, a.out, a.ldo, a.out_bf16, a.act_gelu,
                static_cast<__nv_bfloat16*>(a.copy_bf16), a.ldc, reinterpret_cast<float2*>(a.stat_out), a.stat_groups,
                reinterpret_cast<const float2*>(a.ln_rows), a.ln_colsum, 0, a.batch_rows, nbatch > 1 ? a.b_k_off : 0,
-               a.act_abs, a.conv_pitch, n_run, static_cast<const __nv_bfloat16*>(a.aux), a.ldaux};
+               a.act_abs, a.conv_pitch, n_run, static_cast<const __nv_bfloat16*>(a.aux), a.ldaux,
+               reinterpret_cast<const float2*>(a.shift_rows)};
     const int kb1 = (a.k1 + BK - 1) / BK, kb2 = a.k2 > 0 ? (a.k2 + BK - 1) / BK : 0;
     const int tiles_n = (a.n + n_run - 1) / n_run;      // n_run == BN except for narrow outputs / few-tile problems
     const int tiles_m = pair ? (a.m + 2 * BM - 1) / (2 * BM) : (a.m + BM - 1) / BM;

@@ -11,6 +11,11 @@
 // (x / 255, - mean, / std) written with round-to-nearest intrinsics so nothing is contracted or approximated.
 #include <math.h>
 
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "cvlm_internal.cuh"
@@ -128,6 +133,37 @@ static int ksize_for(int in_size, int out_size) {
     return static_cast<int>(ceil(scale < 1.0 ? 1.0 : scale)) * 2 + 1;
 }
 
+// One pass table in pinned host memory, built once per (input length, output size) and never freed (a few KB to a few MB
+// per distinct image size; bounded to 256 entries, after which the oldest is kept and new sizes fall back to rebuilding
+// into the same slot under the lock -- sizes seen in practice are a handful).
+struct PinnedTable {
+    int* data = nullptr;      // bounds [2 * out] followed by kk [out * ksize]
+    long long n_bounds = 0, n_kk = 0;
+    int ksize = 0;
+};
+static const PinnedTable* pinned_pass_table(int in_size, int out_size) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, PinnedTable> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(in_size, out_size);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    if (cache.size() >= 256) return nullptr;
+    const PassTable t = make_table(in_size, out_size);
+    PinnedTable pt;
+    pt.n_bounds = static_cast<long long>(t.bounds.size());
+    pt.n_kk = static_cast<long long>(t.kk.size());
+    pt.ksize = t.ksize;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&pt.data), static_cast<size_t>(pt.n_bounds + pt.n_kk) * sizeof(int), cudaHostAllocPortable) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    memcpy(pt.data, t.bounds.data(), t.bounds.size() * sizeof(int));
+    memcpy(pt.data + pt.n_bounds, t.kk.data(), t.kk.size() * sizeof(int));
+    return &cache.emplace(key, pt).first->second;
+}
+
 long long preprocess_scratch_bytes(int h, int w, int out_size) {
     const long long tables = (2LL * out_size + static_cast<long long>(out_size) * ksize_for(w, out_size)) * 4 +
                              (2LL * out_size + static_cast<long long>(out_size) * ksize_for(h, out_size)) * 4;
@@ -145,27 +181,29 @@ int preprocess_u8_launch(const unsigned char* img, int h, int w, float* out, int
     unsigned char* mid = static_cast<unsigned char*>(scratch);                      // horizontally resampled image
     int* tab = reinterpret_cast<int*>(mid + align16(static_cast<long long>(h) * out_size * 3));
     const bool need_h = w != out_size, need_v = h != out_size;
-    std::vector<int> host;
-    long long off_hb = 0, off_hk = 0, off_vb = 0, off_vk = 0;
+    // Coefficient tables depend on (input length, output size) only: built once per size and kept in PINNED host memory
+    // (pinned_pass_table), so the upload is a true asynchronous copy on `stream` -- no host serialisation, capturable in a
+    // CUDA graph -- and nothing is rebuilt per image.
+    long long off_hb = 0, off_hk = 0, off_vb = 0, off_vk = 0, used = 0;
     int ks_h = 0, ks_v = 0;
     if (need_h) {
-        const PassTable t = make_table(w, out_size);
-        ks_h = t.ksize;
-        off_hb = static_cast<long long>(host.size());
-        host.insert(host.end(), t.bounds.begin(), t.bounds.end());
-        off_hk = static_cast<long long>(host.size());
-        host.insert(host.end(), t.kk.begin(), t.kk.end());
+        const PinnedTable* t = pinned_pass_table(w, out_size);
+        if (!t) return set_error(CVLM_ERR_CUDA, "preprocess: could not allocate the pinned coefficient table");
+        ks_h = t->ksize;
+        off_hb = used;
+        off_hk = used + t->n_bounds;
+        CVLM_CUDA(cudaMemcpyAsync(tab + used, t->data, static_cast<size_t>(t->n_bounds + t->n_kk) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        used += t->n_bounds + t->n_kk;
     }
     if (need_v) {
-        const PassTable t = make_table(h, out_size);
-        ks_v = t.ksize;
-        off_vb = static_cast<long long>(host.size());
-        host.insert(host.end(), t.bounds.begin(), t.bounds.end());
-        off_vk = static_cast<long long>(host.size());
-        host.insert(host.end(), t.kk.begin(), t.kk.end());
+        const PinnedTable* t = pinned_pass_table(h, out_size);
+        if (!t) return set_error(CVLM_ERR_CUDA, "preprocess: could not allocate the pinned coefficient table");
+        ks_v = t->ksize;
+        off_vb = used;
+        off_vk = used + t->n_bounds;
+        CVLM_CUDA(cudaMemcpyAsync(tab + used, t->data, static_cast<size_t>(t->n_bounds + t->n_kk) * sizeof(int), cudaMemcpyHostToDevice, stream));
+        used += t->n_bounds + t->n_kk;
     }
-    if (!host.empty())   // pageable source: the runtime stages it before returning, so `host` may die at scope exit
-        CVLM_CUDA(cudaMemcpyAsync(tab, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     const unsigned char* vin = img;
     if (need_h) {
         const long long n = static_cast<long long>(h) * out_size;
