@@ -156,6 +156,9 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int y0 = 4 * qb;                          // first grid row of this CTA's queries
     const int tok0 = b * (PLAIN ? L : 4096);
+    // PLAIN: the last query block of a sequence may hold fewer than 129 rows; its second tile is then all padding and is
+    // skipped altogether (no S / PV MMAs, its softmax warpgroup idles): 581 tokens are 4.5 tiles, not 6
+    const int ntile = (PLAIN && qb * 256 + 128 >= L) ? 1 : 2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -244,6 +247,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 const uint64_t k_lo = umma_desc_k_sw128(sK(kst)), k_hi = umma_desc_k_sw128(sK(kst) + G2_KTILE);
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (t >= ntile) break;
                     const uint32_t d = tmem_base + (2 * t + (u & 1)) * 64;
                     const uint64_t q_lo = umma_desc_k_sw128(sQ(t));
 #pragma unroll
@@ -259,6 +263,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 if (u + 1 < NU) issue_s(u + 1);     // runs under the softmax of unit u
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (t >= ntile) break;
                     mbar_wait(p_full(t, u & 1), static_cast<uint32_t>((u >> 1) & 1));   // S_t(u) consumed / P_t(u) written
                     tc_fence_after();
                     if (u >= NREL) {
@@ -274,7 +279,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                             umma_bf16_ts(d, a + 8u * k, v_desc + 128u * k, idescO, (u > NREL || k > 0) ? 1u : 0u);
                         umma_commit(pv_done(t));
                         if (u == NU - 1) umma_commit(o_full(t));
-                        if (t == 1) {
+                        if (t == ntile - 1) {
                             umma_commit(v_empty(vst));
                             if (++vst == G2_VST) { vst = 0; vph ^= 1u; }
                         }
@@ -289,6 +294,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int r = threadIdx.x - 128 - t * 128;
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int qrow = r >> 6, qx = r & 63;
+        if (t < ntile) {
         const uint32_t t_s = tmem_base + lane_addr + t * 128;
         const uint32_t t_o = tmem_base + lane_addr + G2_COL_O + t * G2_O_STRIDE;
         float trow[PLAIN ? 1 : 256];                // this row of T_w (0..127) and T_h (128..255): dynamic indexing -> local memory
@@ -426,6 +432,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 *reinterpret_cast<uint4*>(orow + 64 + i) = o4;
             }
         }
+        }   // t < ntile
     }
     tc_fence_before();
     __syncthreads();
