@@ -49,6 +49,13 @@ constexpr int G2_THREADS = 384;
 constexpr uint32_t G2_COL_O = 256, G2_O_STRIDE = 80;
 constexpr float kLog2eG2 = 1.4426950408889634f;
 constexpr float G2_UNIT_LIMIT = 1073741824.0f;     // 2^30
+// Bottleneck probes (tools/attn_probe.sh builds side libraries with -DG2_PROBE=n; the shipped library has 0):
+// bit 0 = the softmax warps skip the exponentials (P = raw S bits), bit 1 = K / V units are loaded for the first
+// ring fill only and the MMAs re-read those stages (no steady-state TMA traffic), bit 2 = the 16-wide d 64..79 boxes of
+// K and V are not loaded (half the TMA box rows).  Results are garbage by design.
+#ifndef G2_PROBE
+#define G2_PROBE 0
+#endif
 
 // 2^x for a pair on the FMA pipe: n = round(x), r = x - n in [-0.5, 0.5], cubic in r, exponent added as an integer.
 __device__ __forceinline__ void g2_exp2_poly(uint64_t x2, float& p0, float& p1) {
@@ -205,8 +212,10 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             int kst = 0, vst = 0;
             uint32_t kph = 0, vph = 0;
             auto produce_k = [&](int u) {
+                if ((G2_PROBE & 2) && u >= NREL + G2_KST) return;
                 mbar_wait(k_empty(kst), kph ^ 1u);
-                mbar_arrive_expect_tx(k_full(kst), KV_BYTES);
+                const bool skip_hi = (G2_PROBE & 4) && u >= NREL;     // probe: 64 box rows per unit instead of 128
+                mbar_arrive_expect_tx(k_full(kst), skip_hi ? G2_KTILE : KV_BYTES);
                 if (!PLAIN && u < 2) {
                     tma_load_2d(sK(kst), &tmRelW, k_full(kst), 0, u * 64);
                     if (HI) tma_load_2d(sK(kst) + G2_KTILE, &tmRelW, k_full(kst), 64, u * 64);
@@ -216,16 +225,17 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 } else {
                     const int tok = tok0 + (u - NREL) * G2_UNIT;
                     tma_load_3d(sK(kst), &tmKV, k_full(kst), 0, heads + head, tok);
-                    if (HI) tma_load_3d(sK(kst) + G2_KTILE, &tmKV, k_full(kst), 64, heads + head, tok);
+                    if (HI && !skip_hi) tma_load_3d(sK(kst) + G2_KTILE, &tmKV, k_full(kst), 64, heads + head, tok);
                 }
                 if (++kst == G2_KST) { kst = 0; kph ^= 1u; }
             };
             auto produce_v = [&](int j) {
+                if ((G2_PROBE & 2) && j >= G2_VST) return;
                 mbar_wait(v_empty(vst), vph ^ 1u);
-                mbar_arrive_expect_tx(v_full(vst), KV_BYTES);
+                mbar_arrive_expect_tx(v_full(vst), (G2_PROBE & 4) ? G2_KTILE : KV_BYTES);
                 const int tok = tok0 + j * G2_UNIT;
                 tma_load_3d(sV(vst), &tmKV, v_full(vst), 0, 2 * heads + head, tok);
-                if (HI) tma_load_3d(sV(vst) + G2_KTILE, &tmKV, v_full(vst), 64, 2 * heads + head, tok);
+                if (HI && !(G2_PROBE & 4)) tma_load_3d(sV(vst) + G2_KTILE, &tmKV, v_full(vst), 64, 2 * heads + head, tok);
                 if (++vst == G2_VST) { vst = 0; vph ^= 1u; }
             };
             for (int u = 0; u < NREL; ++u) produce_k(u);
@@ -242,7 +252,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             int kst = 0, vst = 0;
             uint32_t kph = 0, vph = 0;
             auto issue_s = [&](int u) {             // S_t(u) for both query tiles into buffer u & 1
-                mbar_wait(k_full(kst), kph);
+                if (!(G2_PROBE & 2) || u < NREL + G2_KST) mbar_wait(k_full(kst), kph);
                 tc_fence_after();
                 const uint64_t k_lo = umma_desc_k_sw128(sK(kst)), k_hi = umma_desc_k_sw128(sK(kst) + G2_KTILE);
 #pragma unroll
@@ -250,6 +260,14 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     if (t >= ntile) break;
                     const uint32_t d = tmem_base + (2 * t + (u & 1)) * 64;
                     const uint64_t q_lo = umma_desc_k_sw128(sQ(t));
+                    if (G2_PROBE & 8) {         // probe: A operand from (uninitialised) tensor memory instead of shared memory
+                        const uint32_t qa = tmem_base + 416 + 40 * t;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16_ts(d, qa + 8u * k, k_lo + 2u * k, idescS, k > 0);
+                        if (HI) umma_bf16_ts(d, qa + 32u, k_hi, idescS, 1);
+                        umma_commit(s_full(t, u & 1));
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16_ss(d, q_lo + 2u * k, k_lo + 2u * k, idescS, k > 0);
                     if (HI) umma_bf16_ss(d, umma_desc_k_sw128(sQ(t) + G2_QTILE), k_hi, idescS, 1);
@@ -267,7 +285,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     mbar_wait(p_full(t, u & 1), static_cast<uint32_t>((u >> 1) & 1));   // S_t(u) consumed / P_t(u) written
                     tc_fence_after();
                     if (u >= NREL) {
-                        if (t == 0) {
+                        if (t == 0 && (!(G2_PROBE & 2) || u - NREL < G2_VST)) {
                             mbar_wait(v_full(vst), vph);
                             tc_fence_after();
                         }
@@ -350,7 +368,13 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             }
             uint32_t pk[32];
             uint64_t acc0 = 0ull, acc1 = 0ull;
-            {
+            if (G2_PROBE & 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    pk[i] = va[2 * i] & 0x3f803f80u;
+                    pk[16 + i] = vb[2 * i] & 0x3f803f80u;
+                }
+            } else {
                 const float ch = th - m_used;
                 const uint64_t ch2 = f32x2_pack(ch, ch);
                 g2_chunk_exp<0, POLY>(va, tw2, ch2, scale2, acc0, acc1, pk);

@@ -49,6 +49,12 @@ constexpr int W2_REL_H = 196, W2_REL_W = 223;        // K' rows / S' columns of 
 constexpr uint32_t W2_COL_O = 112;
 constexpr float kLog2eW2 = 1.4426950408889634f;
 constexpr float W2_CHUNK_LIMIT = 1073741824.0f;      // 2^30
+// Bottleneck probes (tools/attn_probe.sh builds side libraries with -DW2_PROBE=n; the shipped library has 0):
+// bit 0 = no exponentials (P = masked S bits), bit 1 = Q / K / V are loaded for the first item only, bit 2 = the
+// d 64..79 boxes are not loaded (half the TMA box rows), bit 3 = no global stores.  Results are garbage by design.
+#ifndef W2_PROBE
+#define W2_PROBE 0
+#endif
 
 struct Win2Item {
     int b, wy, wx, head, ntiles;
@@ -63,7 +69,9 @@ __device__ __forceinline__ float w2_chunk_exp(const uint32_t* v, const uint64_t 
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         const int k0 = C * 32 + 2 * i;
-        if (k0 < W2_L) {
+        if (W2_PROBE & 1) {
+            pk[i] = v[2 * i] & 0x3f803f80u;
+        } else if (k0 < W2_L) {
             const uint64_t a = f32x2_add(tw2[(k0 % W2_WS) / 2], thm2[k0 / W2_WS]);
             const uint64_t x = f32x2_fma(f32x2_pack_bits(v[2 * i], v[2 * i + 1]), scale2, a);
             float x0, x1;
@@ -134,7 +142,8 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                        const __nv_bfloat16* __restrict__ relw, __nv_bfloat16* __restrict__ out, int G, int nW, int heads,
                        int D, int num_items, float scale_log2) {
     constexpr bool HI = HD > 64;
-    constexpr uint32_t LOAD_BYTES = (HI ? 2 : 1) * W2_BOX_BYTES;
+    constexpr bool LOAD_HI = HI && !(W2_PROBE & 4);
+    constexpr uint32_t LOAD_BYTES = (LOAD_HI ? 2 : 1) * W2_BOX_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -218,18 +227,19 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 const Win2Item w = decode(it);
                 const uint32_t ph = static_cast<uint32_t>(n & 1);          // one slot each: the phase flips per item
                 const int x0 = w.wx * W2_WS, y0 = w.wy * W2_WS;
+                if ((W2_PROBE & 2) && n > 0) break;
                 mbar_wait(q_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(q_full, LOAD_BYTES);
                 tma_load_5d(sQ, &tmQKV, q_full, 0, w.head, x0, y0, w.b);
-                if (HI) tma_load_5d(sQ + W2_TILE, &tmQKV, q_full, 64, w.head, x0, y0, w.b);
+                if (LOAD_HI) tma_load_5d(sQ + W2_TILE, &tmQKV, q_full, 64, w.head, x0, y0, w.b);
                 mbar_wait(k_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(k_full, LOAD_BYTES);
                 tma_load_5d(sK, &tmQKV, k_full, 0, heads + w.head, x0, y0, w.b);
-                if (HI) tma_load_5d(sK + W2_KTILE, &tmQKV, k_full, 64, heads + w.head, x0, y0, w.b);
+                if (LOAD_HI) tma_load_5d(sK + W2_KTILE, &tmQKV, k_full, 64, heads + w.head, x0, y0, w.b);
                 mbar_wait(v_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(v_full, LOAD_BYTES);
                 tma_load_5d(sV, &tmQKV, v_full, 0, 2 * heads + w.head, x0, y0, w.b);
-                if (HI) tma_load_5d(sV + W2_TILE, &tmQKV, v_full, 64, 2 * heads + w.head, x0, y0, w.b);
+                if (LOAD_HI) tma_load_5d(sV + W2_TILE, &tmQKV, v_full, 64, 2 * heads + w.head, x0, y0, w.b);
             }
         } else if (warp == 1 && elect_one_sync()) {
             // ============================================================ MMA issuer
@@ -241,8 +251,10 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
             uint32_t uses[2] = {0, 0};               // how many times tile t has been processed
             for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
                 const Win2Item w = decode(it);
-                mbar_wait(q_full, static_cast<uint32_t>(n & 1));
-                mbar_wait(k_full, static_cast<uint32_t>(n & 1));
+                if (!(W2_PROBE & 2) || n == 0) {
+                    mbar_wait(q_full, static_cast<uint32_t>(n & 1));
+                    mbar_wait(k_full, static_cast<uint32_t>(n & 1));
+                }
                 tc_fence_after();
                 for (int t = 0; t < w.ntiles; ++t) {
                     if (uses[t] > 0) {
@@ -262,7 +274,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 for (int t = 0; t < w.ntiles; ++t) {
                     mbar_wait(p_full(t), uses[t] & 1u);
                     tc_fence_after();
-                    if (t == 0) {
+                    if (t == 0 && (!(W2_PROBE & 2) || n == 0)) {
                         mbar_wait(v_full, static_cast<uint32_t>(n & 1));
                         tc_fence_after();
                     }
@@ -369,7 +381,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 // item's S' cannot start until this arrives (timeline: the stores took ~1800 of ~9100 cycles per item)
                 tc_fence_before();
                 mbar_arrive(o_empty(t));
-                if (store) {
+                if (store && !(W2_PROBE & 8)) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 16) {
                         uint32_t pk[8];
