@@ -362,13 +362,24 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    e_enc = torch.cuda.Event(enable_timing=True)
     for _ in range(K):
         step(x_dev)
+    e_enc.record()          # this rank's encoders are enqueued; the gathers run on the side stream
     drain()
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    by_rank = None
+    if world > 1:
+        # where the scaling efficiency goes: every rank's own encoder time (GPU-to-GPU spread, SMs lent to NCCL) next to
+        # its time including the wait for the last gather
+        t = torch.tensor([e0.elapsed_time(e_enc) / K, e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        by_rank = {"encoder_ms_per_step": [round(float(a[0]), 3) for a in allt],
+                   "with_gather_ms_per_step": [round(float(a[1]), 3) for a in allt]}
     launches = model.last_launch_count * K * n_micro
     value = world * per_rank * K / (ms_total * 1e-3)
     gather_info = None
@@ -377,6 +388,7 @@ def run_ours(args):
                        (world - 1) * per_rank * tail[0] * tail[1] * tail[2] * (2 if gdtype == torch.bfloat16 else 4),
                        "how": "dist.ChunkGatherer: all_gather of each micro-batch's embeddings on a side stream under the "
                               "next micro-batch's encoder; the timed region waits for the last one"}
+        gather_info["by_rank"] = by_rank
     gatherers = None
 
     def plain_step(x):
