@@ -363,6 +363,10 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
             ga.m = static_cast<int>(M); ga.n = D; ga.bias = static_cast<const float*>(fold ? l2bf : l2b);
             ga.residual = xcur; ga.ldr = D; ga.out = dst; ga.ldo = D;
             if (fold) feeds_norm(ga, i + 1, i);   // otherwise prompt_add below writes the next norm1 input
+            if (last) {   // the neck's 1x1 conv reads bf16(x): let this epilogue write it (unshifted producer copy; the
+                          // statistics land in the scratch and are not used) instead of a separate cast pass
+                ga.copy_bf16 = a; ga.ldc = D; ga.stat_out = stat; ga.stat_groups = sgroups;
+            }
             CVLM_TRY(f.gemm(K_GEMM_LIN2, ga));
             if (fold) CVLM_TRY(finalize_norm(i + 1));
         }
@@ -385,9 +389,8 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
     CVLM_TRY(f.get("neck.conv2.w", 2LL * OC * 9 * OC, &c2w));
     CVLM_TRY(f.get("neck.ln2.w", 4LL * OC, &n2w));
     CVLM_TRY(f.get("neck.ln2.b", 4LL * OC, &n2b));
-    CVLM_TRY(f.run(K_OTHER, [&] { return cast_bf16_launch(xcur, a, M * D, stream); }));
-    // n1 / n2 live in the (now dead) x region unless the final residual stream is x itself being read...
-    // the cast above already consumed it, so the region is free either way.
+    // `a` holds bf16(x) already (written by the last lin2); n1 / n2 live in the x region, which is dead by now unless the
+    // final residual stream is x itself -- and then nothing reads it any more either.
     float* n1 = train ? reinterpret_cast<float*>(svb + sv.off_n1) : x;
     float* n2 = train ? reinterpret_cast<float*>(svb + sv.off_n2) : x + M * OC;
     {   // 1x1 conv, no bias

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(128) adapter_embed_kernel(const float* __restr
                                                             const float* __restrict__ w_t, const float* __restrict__ cst,
                                                             __nv_bfloat16* __restrict__ t_out, int T, int D, int rank) {
     constexpr int CHUNK = 64;
-    __shared__ float sw[CHUNK * RP];
+    __shared__ __align__(16) float sw[CHUNK * RP];
+    static_assert(RP % 4 == 0, "adapter_embed: float4 weight reads");
     const int b = blockIdx.y;
     const int tp = blockIdx.x * 128 + threadIdx.x;
     const bool ok = tp < T;
@@ -285,7 +286,25 @@ __global__ void __launch_bounds__(128) adapter_embed_kernel(const float* __restr
         __syncthreads();
         if (ok) {
             const int cend = D - c0 < CHUNK ? D - c0 : CHUNK;
-            for (int c = 0; c < cend; ++c) {
+            int c = 0;
+            for (; c + 8 <= cend; c += 8) {          // eight independent loads in flight, then 8 x RP FMAs
+                float xv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xv[k] = __ldg(xb + static_cast<long long>(c0 + c + k) * T + tp);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4* w4 = reinterpret_cast<const float4*>(sw + (c + k) * RP);
+#pragma unroll
+                    for (int j = 0; j < RP; j += 4) {
+                        const float4 w = w4[j / 4];
+                        acc[j] = fmaf(w.x, xv[k], acc[j]);
+                        acc[j + 1] = fmaf(w.y, xv[k], acc[j + 1]);
+                        acc[j + 2] = fmaf(w.z, xv[k], acc[j + 2]);
+                        acc[j + 3] = fmaf(w.w, xv[k], acc[j + 3]);
+                    }
+                }
+            }
+            for (; c < cend; ++c) {
                 const float xv = __ldg(xb + static_cast<long long>(c0 + c) * T + tp);
 #pragma unroll
                 for (int j = 0; j < RP; ++j) acc[j] = fmaf(sw[c * RP + j], xv, acc[j]);
