@@ -179,6 +179,7 @@ class ImageEncoderViT(nn.Module):
         # hard-coded by the reference, image_encoder.py:116-123
         self.scale_factor = 32
         self.prompt_type = 'highpass'
+        self.high_pass = "gemm"      # or "fft": PromptGenerator.fft through torch.fft in fp32 (see _run)
         self.tuning_stage = 1234
         self.input_type = 'fft'
         self.freq_nums = 0.25
@@ -349,10 +350,21 @@ class ImageEncoderViT(nn.Module):
             if interms:
                 arr = (C.c_void_p * len(interms))(*[t[s:e].data_ptr() for t in interms])
                 iptr = C.cast(arr, C.POINTER(C.c_void_p))
-            # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu)
+            # highpass = NULL: PromptGenerator.fft runs inside the library (csrc/highpass.cu: two bf16 GEMMs with the
+            # low-pass projector, absolute error ~1.6e-3 of the image's RMS).  high_pass = "fft" hands the library an fp32
+            # torch.fft result instead: for images whose content above a quarter of the sampling rate is weaker than
+            # that (smooth / defocused photographs), see DESIGN.md section 5.2.
+            hp = None
+            if self.high_pass == "fft":
+                from .check_path import high_pass as _hp_fft
+                with torch.cuda.device(x.device):
+                    hp = _hp_fft(xc, self._cfg.freq_nums).contiguous()
+            elif self.high_pass != "gemm":
+                raise ValueError(f"high_pass must be 'gemm' or 'fft', not {self.high_pass!r}")
             with torch.cuda.device(x.device):       # the C ABI launches on the CUDA current device
-                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None, e - s, out[s:e].data_ptr(), iptr,
-                                                    ws.data_ptr(), ws.numel(), stream), "cvlm_encoder_forward")
+                _lib.check(lib.cvlm_encoder_forward(self._handle, xc.data_ptr(), None if hp is None else hp.data_ptr(),
+                                                    e - s, out[s:e].data_ptr(), iptr, ws.data_ptr(), ws.numel(), stream),
+                           "cvlm_encoder_forward")
             launches += lib.cvlm_encoder_last_launch_count(self._handle)
         self.last_launch_count = launches
 
@@ -399,7 +411,8 @@ class ImageEncoderViT(nn.Module):
 
         if out_host is None:
             out_host = torch.empty(B, cfg.out_chans, g, g, dtype=torch.float32, pin_memory=True)
-        if on_chunk is None and x_host.dtype == torch.float32 and x_host.is_contiguous() and out_host.is_contiguous():
+        if (on_chunk is None and self.high_pass == "gemm" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+                and out_host.is_contiguous()):
             # the whole pipeline in ONE C-ABI call (cvlm_encoder_forward_host): same copies, same stream choreography
             self._ensure_ready(dev)
             lib = _lib.load()

@@ -249,3 +249,57 @@ def test_rows_with_large_mean_and_outlier_channels(offset, outlier):
     err_i = max(orc.rel_l2(a.cpu(), b) for a, b in zip(interm, want_i))
     print(f"offset {offset} outlier {outlier}: embedding rel-L2 {err:.3e}, interm {err_i:.3e}")
     assert err < BF16_TOL and err_i < BF16_TOL
+
+
+def _pink_images(batch, n, alpha, mean, seed):
+    """Images with a 1/f^alpha amplitude spectrum (alpha = 1 is the textbook natural-image statistic), unit variance."""
+    g = torch.Generator().manual_seed(seed)
+    fy = torch.fft.fftfreq(n)[:, None]
+    fx = torch.fft.fftfreq(n)[None, :]
+    f = (fy ** 2 + fx ** 2).sqrt()
+    f[0, 0] = 1.0
+    amp = f ** (-alpha)
+    amp[0, 0] = 0.0
+    phase = torch.rand(batch, 3, n, n, generator=g) * (2 * np.pi)
+    x = torch.fft.ifft2(amp * torch.exp(1j * phase)).real
+    x = (x - x.mean(dim=(-2, -1), keepdim=True)) / x.std(dim=(-2, -1), keepdim=True) + mean
+    return x.float()
+
+
+@pytest.mark.parametrize("alpha,rel_gate", [(1.0, 1e-2), (1.5, 8e-2)])
+def test_high_pass_on_natural_image_spectra(alpha, rel_gate):
+    """X - P X P^T is a large-minus-large step when most of the image's energy sits below a quarter of
+    the sampling rate.  The bf16 projector route has an ABSOLUTE error of ~1.6e-3 of the image's RMS whatever the
+    spectrum (bf16 rounding of X, of P and of the intermediate Y, emulated on the CPU in DESIGN.md section 5.2), i.e.
+    0.5 % of the high-pass signal for a 1/f image and ~4 % for a 1/f^1.5 one; the fp32 FFT route (high_pass = "fft") is exact."""
+    from camouflaged_vlm_b200 import check_path as cp
+    from camouflaged_vlm_b200 import ops
+    from camouflaged_vlm_b200.packing import high_pass_matrices
+    n = 1024
+    x = _pink_images(1, n, alpha, 0.5, 11).cuda()
+    pcat, npr, pi = high_pass_matrices(n, 0.25, "cuda")
+    got = ops.high_pass(x, pcat, npr, pi)
+    want = cp.high_pass(x, 0.25)
+    err = (got - want).pow(2).mean().sqrt().item()
+    assert err < 3e-3 * x.pow(2).mean().sqrt().item()
+    assert orc.rel_l2(got.cpu(), want.cpu()) < rel_gate
+
+
+def test_encoder_high_pass_fft_mode():
+    """high_pass = "fft": the library takes the caller's fp32 high-pass instead of running its projector GEMMs; on the
+    reference fixture both modes meet the gate, and they differ from each other by less than the gate."""
+    cfg = PRESETS["small_hd80"]
+    g = np.load(os.path.join(GOLDEN, "encoder_small_hd80.npz"))
+    m = _encoder(cfg)
+    x = seeded_images(cfg, 1).cuda()
+    with torch.no_grad():
+        a = m(x)
+        m.high_pass = "fft"
+        b = m(x)
+        m.high_pass = "nope"
+        with pytest.raises(ValueError):
+            m(x)
+    want = torch.from_numpy(g["out"])
+    assert orc.rel_l2(a.cpu(), want) < BF16_TOL and orc.rel_l2(b.cpu(), want) < BF16_TOL
+    assert orc.rel_l2(a.cpu(), b.cpu()) < BF16_TOL
+    assert not torch.equal(a, b)
