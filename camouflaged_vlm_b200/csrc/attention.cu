@@ -400,7 +400,8 @@ static int launch_attention(const AttnParams& p, int batch, cudaStream_t stream)
 }
 
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                     int window, int heads, int head_dim, cudaStream_t stream) {
+                     int window, int heads, int head_dim, cudaStream_t stream, float* lse_out, bool* lse_written) {
+    if (lse_written) *lse_written = false;
     if (!qkv || !out || !relh || !relw) return set_error(CVLM_ERR_ARG, "attention: null pointer");
     if (batch <= 0 || grid_side <= 0 || heads <= 0) return set_error(CVLM_ERR_ARG, "attention: bad sizes");
     if (head_dim != 32 && head_dim != 64 && head_dim != 80)
@@ -423,10 +424,14 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     // 64x64 global blocks and 14x14 windows run on the tcgen05 kernels (attention_tc2.cu, attention_tc_win2.cu);
     // cvlm_set_option("attn_legacy", 1) (or CVLM_ATTN_LEGACY=1 at start-up) forces the mma.sync kernel below (A/B comparisons, bisecting).
     const bool legacy = option(OPT_ATTN_LEGACY) != 0;
-    if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80))
-        return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream);
-    if (!legacy && window == 14 && (head_dim == 64 || head_dim == 80))
-        return attention_window_tc2_launch(qkv, out, relh, relw, batch, grid_side, heads, head_dim, stream);
+    if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80)) {
+        if (lse_written) *lse_written = lse_out != nullptr;
+        return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream, lse_out);
+    }
+    if (!legacy && window == 14 && (head_dim == 64 || head_dim == 80)) {
+        if (lse_written) *lse_written = lse_out != nullptr;
+        return attention_window_tc2_launch(qkv, out, relh, relw, batch, grid_side, heads, head_dim, stream, lse_out);
+    }
     const bool aligned = (p.S == ATT_BK);
     if (head_dim == 80)
         return aligned ? launch_attention<80, true>(p, batch, stream) : launch_attention<80, false>(p, batch, stream);

@@ -43,6 +43,7 @@ struct BwdParams {
     const __nv_bfloat16* relw;
     int G, S, nW, heads, D, TWP, TWK;
     float scale, scale_log2;
+    int lse_ready;              // lse was written by the forward kernel: the specialised kernels skip their own S sweep for it
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -866,7 +867,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq64_kernel(const BwdP
         }
     };
 
-    // ---- pass 1: row log-sum-exp (K tiles only)
+    // ---- pass 1: row log-sum-exp (K tiles only) -- unless the training forward left it (BwdParams::lse_ready)
+    float lse[2];
+    if (p.lse_ready) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) lse[h] = p.lse[(tok_base + qt * 64 + warp * 16 + g + h * 8) * p.heads + head];
+    } else {
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     load_tile(0, 0, false);
     cp_async_commit();
@@ -899,13 +905,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq64_kernel(const BwdP
         }
         __syncthreads();
     }
-    float lse[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
         l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
         lse[h] = m_run[h] + log2f(l_run[h]);
         if (t == 0) p.lse[(tok_base + qt * 64 + warp * 16 + g + h * 8) * p.heads + head] = lse[h];
+    }
     }
 
     // ---- pass 2
@@ -1427,7 +1433,15 @@ __global__ void __launch_bounds__(WB_THREADS, 1) attn_bwd_win14_kernel(const Bwd
             }
     };
     float lse[2];
-    {
+    if (p.lse_ready) {          // left by the training forward; rows that are not tokens of the grid take no part (P = 0)
+        const int gt0 = sGt[r0], gt1 = sGt[r1];
+        lse[0] = gt0 >= 0 ? p.lse[(tok_base + gt0) * p.heads + head] : INFINITY;
+        lse[1] = gt1 >= 0 ? p.lse[(tok_base + gt1) * p.heads + head] : INFINITY;
+        if (t == 0) {
+            sLse[r0] = lse[0];
+            sLse[r1] = lse[1];
+        }
+    } else {
         float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 #pragma unroll 1
         for (int np = 0; np < NP; ++np) {
@@ -1704,7 +1718,7 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
 // Every element of dqkv that belongs to a token of the grid is written (2 launches).
 int attention_backward_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
                               const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
-                              int head_dim, cudaStream_t stream) {
+                              int head_dim, cudaStream_t stream, bool lse_ready) {
     if (!qkv || !o || !dout || !dqkv || !lse || !dsum || !relh || !relw)
         return set_error(CVLM_ERR_ARG, "attention_backward: null pointer");
     if (batch <= 0 || grid_side <= 0 || heads <= 0) return set_error(CVLM_ERR_ARG, "attention_backward: bad sizes");
@@ -1714,6 +1728,7 @@ int attention_backward_launch(const void* qkv, const void* o, const void* dout, 
     p.dout = static_cast<const __nv_bfloat16*>(dout);
     p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
     p.lse = lse;
+    p.lse_ready = lse_ready ? 1 : 0;
     p.dsum = dsum;
     p.relh = static_cast<const __nv_bfloat16*>(relh);
     p.relw = static_cast<const __nv_bfloat16*>(relw);

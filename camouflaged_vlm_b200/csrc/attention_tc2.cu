@@ -134,7 +134,8 @@ template <int HD, int POLY, bool PLAIN>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmRelH, const __grid_constant__ CUtensorMap tmRelW,
-                       __nv_bfloat16* __restrict__ out, int heads, int D, float scale_log2, int L) {
+                       __nv_bfloat16* __restrict__ out, int heads, int D, float scale_log2, int L,
+                       float* __restrict__ lse_out) {
     constexpr bool HI = HD > 64;
     constexpr uint32_t Q_BYTES = (HI ? 2 : 1) * G2_QTILE;
     constexpr uint32_t KV_BYTES = (HI ? 2 : 1) * G2_KTILE;
@@ -427,6 +428,9 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const float inv = 1.0f / l;
         __nv_bfloat16* orow = out + (static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * D + head * HD;
         const bool live = !PLAIN || qb * 256 + t * 128 + r < L;        // query rows beyond the sequence are not stored
+        // training forward: the row's log-sum-exp (log2 domain, rel-pos terms included) for the backward kernels
+        if (lse_out != nullptr && live)
+            lse_out[(static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head] = m_used + log2f(l);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             tmem_ld_32x32(t_o + c * 32, va);
@@ -468,7 +472,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <int HD, int POLY, bool PLAIN>
 static int launch_global_tc2(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                             int tokens, cudaStream_t stream) {
+                             int tokens, cudaStream_t stream, float* lse_out = nullptr) {
     const int D = heads * HD;
     CUtensorMap tq, tkv, th, tw;
     MapSpec s = map_spec_zero();
@@ -510,20 +514,20 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
     CVLM_TRY(ensure_dynamic_smem(kern, G2_SMEM, ready));
     dim3 grid((tokens + 255) / 256, heads, batch);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eG2;
-    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens);
+    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens, lse_out);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
 
 template <int HD>
 static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const void* relh, const void* relw, int batch,
-                                  int heads, cudaStream_t stream) {
+                                  int heads, cudaStream_t stream, float* lse_out) {
     switch (poly) {
-        case 0: return launch_global_tc2<HD, 0, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
-        case 2: return launch_global_tc2<HD, 2, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
-        case 4: return launch_global_tc2<HD, 4, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
-        case 6: return launch_global_tc2<HD, 6, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
-        case 8: return launch_global_tc2<HD, 8, false>(qkv, out, relh, relw, batch, heads, 4096, stream);
+        case 0: return launch_global_tc2<HD, 0, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
+        case 2: return launch_global_tc2<HD, 2, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
+        case 4: return launch_global_tc2<HD, 4, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
+        case 6: return launch_global_tc2<HD, 6, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
+        case 8: return launch_global_tc2<HD, 8, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
         default: return set_error(CVLM_ERR_ARG, "CVLM_ATTN_POLY must be 0, 2, 4, 6 or 8");
     }
 }
@@ -531,11 +535,11 @@ static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const vo
 // Global attention over a 64x64 token grid, head_dim 64 or 80.
 // CVLM_ATTN_POLY = how many of every 16 exponential pairs run on the FMA pipe (tuning knob; default below).
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                                int head_dim, cudaStream_t stream) {
+                                int head_dim, cudaStream_t stream, float* lse_out) {
     if (batch > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch exceeds grid.z; split the batch");
     const int poly = option(OPT_ATTN_POLY);               // cvlm_set_option("attn_poly", n); default 4
-    if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream);
-    if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream);
+    if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out);
+    if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: head_dim %d", head_dim);
 }
 

@@ -140,7 +140,7 @@ template <int HD>
 __global__ void __launch_bounds__(W2_THREADS, 1)
 attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ relh,
                        const __nv_bfloat16* __restrict__ relw, __nv_bfloat16* __restrict__ out, int G, int nW, int heads,
-                       int D, int num_items, float scale_log2) {
+                       int D, int num_items, float scale_log2, float* __restrict__ lse_out) {
     constexpr bool HI = HD > 64;
     constexpr bool LOAD_HI = HI && !(W2_PROBE & 4);
     constexpr uint32_t LOAD_BYTES = (LOAD_HI ? 2 : 1) * W2_BOX_BYTES;
@@ -308,7 +308,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
             if (t >= w.ntiles) continue;
             mbar_wait(s_full(t), use & 1u);
             tc_fence_after();
-            float l = 1.f;
+            float l = 1.f, m_row = 0.f;
             if (warp_active) {
                 // ---- this row of T = q . [rel_pos_h ; rel_pos_w]: S' columns 192..255 hold keys 192..195, T_h, T_w
                 uint32_t va[32], vb[32];
@@ -356,6 +356,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
 #pragma unroll
                 for (int i = 0; i < 16; ++i) tail16[i] = i < 4 ? tail[i] : 0u;
                 w2_chunk<6, 8>(tail16, tw, th, tw2, thm2, m_used, l, scale2, scale_log2, t_s, q_in_window);
+                m_row = m_used;
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -381,6 +382,9 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 // item's S' cannot start until this arrives (timeline: the stores took ~1800 of ~9100 cycles per item)
                 tc_fence_before();
                 mbar_arrive(o_empty(t));
+                // training forward: the row's log-sum-exp (log2 domain, rel-pos terms included) for the backward kernels
+                if (store && lse_out != nullptr)
+                    lse_out[((static_cast<long long>(w.b) * G + gy) * G + gx) * heads + w.head] = m_row + log2f(l);
                 if (store && !(W2_PROBE & 8)) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 16) {
@@ -422,7 +426,7 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
 
 template <int HD>
 static int launch_window_tc2(const void* qkv, void* out, const void* relh, const void* relw, int batch, int G, int heads,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, float* lse_out) {
     const int D = heads * HD;
     const int nW = (G + W2_WS - 1) / W2_WS;
     CUtensorMap tq;
@@ -455,16 +459,16 @@ static int launch_window_tc2(const void* qkv, void* out, const void* relh, const
     const int grid = items < sms ? items : sms;
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eW2;
     kern<<<grid, W2_THREADS, W2_SMEM, stream>>>(tq, static_cast<const __nv_bfloat16*>(relh), static_cast<const __nv_bfloat16*>(relw),
-                                                static_cast<__nv_bfloat16*>(out), G, nW, heads, D, items, scale_log2);
+                                                static_cast<__nv_bfloat16*>(out), G, nW, heads, D, items, scale_log2, lse_out);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
 
 // 14x14 window attention, head_dim 64 or 80, any token grid.
 int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                                int heads, int head_dim, cudaStream_t stream) {
-    if (head_dim == 80) return launch_window_tc2<80>(qkv, out, relh, relw, batch, grid_side, heads, stream);
-    if (head_dim == 64) return launch_window_tc2<64>(qkv, out, relh, relw, batch, grid_side, heads, stream);
+                                int heads, int head_dim, cudaStream_t stream, float* lse_out) {
+    if (head_dim == 80) return launch_window_tc2<80>(qkv, out, relh, relw, batch, grid_side, heads, stream, lse_out);
+    if (head_dim == 64) return launch_window_tc2<64>(qkv, out, relh, relw, batch, grid_side, heads, stream, lse_out);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_window_tc2: head_dim %d", head_dim);
 }
 

@@ -100,22 +100,27 @@ struct GemmArgs {
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
 // ---- attention (attention.cu)
+// lse_out (optional, training forward): fp32 [batch * grid^2, heads], every token's row log-sum-exp in the log2 domain;
+// *lse_written tells whether the kernel that ran produces it (the tcgen05 kernels do, the mma.sync fallback does not).
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                     int window, int heads, int head_dim, cudaStream_t stream);
+                     int window, int heads, int head_dim, cudaStream_t stream, float* lse_out = nullptr,
+                     bool* lse_written = nullptr);
 
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                                int head_dim, cudaStream_t stream);
+                                int head_dim, cudaStream_t stream, float* lse_out = nullptr);
 
 int attention_plain_tc2_launch(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
                                cudaStream_t stream);
 
 int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                                int heads, int head_dim, cudaStream_t stream);
+                                int heads, int head_dim, cudaStream_t stream, float* lse_out = nullptr);
 
 // ---- backward pass for adapter-only training (attention_bwd.cu, backward.cu)
+// lse_ready: `lse` already holds the forward's row log-sum-exp (attention_launch's lse_out); the kernels then skip their
+// own sweep over S that would compute it.
 int attention_backward_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
                               const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
-                              int head_dim, cudaStream_t stream);
+                              int head_dim, cudaStream_t stream, bool lse_ready = false);
 int layernorm_train_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, void* xhat_bf16,
                            float* rstd, long long rows, int cols, float eps, cudaStream_t stream);
 int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void* xsrc, const float* stat,

@@ -134,6 +134,7 @@ Saved plan_saved(const cvlm_encoder_config& c, int batch) {
     s.b_xh2 = take(M * D * 2);
     s.b_rstd2 = take(M * 4);
     s.b_hpre = take(M * c.mlp_dim * 2);
+    s.b_lse = take(M * c.num_heads * 4);
     s.block_stride = off;
     s.total = s.off_blocks + s.block_stride * c.depth;
     return s;
@@ -320,7 +321,13 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
             CVLM_TRY(f.gemm(K_GEMM_QKV, ga));
         }
         CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
-            return attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream);
+            if (!train) return attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream);
+            // the backward kernels need every row's log-sum-exp: the tcgen05 kernels leave it next to the activations
+            bool wrote = false;
+            const int rc = attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream,
+                                            reinterpret_cast<float*>(blk_ptr(i, sv.b_lse)), &wrote);
+            enc->lse_saved[i] = wrote ? 1 : 0;
+            return rc;
         }));
         {   // proj (:502) + shortcut (:443); bias = b_proj + W_proj * b_v
             GemmArgs ga;

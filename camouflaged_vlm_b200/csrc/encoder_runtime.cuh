@@ -28,6 +28,8 @@ struct cvlm_encoder {
     std::vector<ProfSpan> spans;        // spans of the profiled forwards since the last get_profile
     std::vector<cudaEvent_t> event_pool;
     std::vector<cudaEvent_t> host_events;   // cvlm_encoder_forward_host: staging-buffer ready / consumed, stream edges
+    // training forward: block i's attention kernel left the row log-sum-exp in the saved region (the tcgen05 kernels do)
+    unsigned char lse_saved[CVLM_MAX_DEPTH] = {};
 };
 
 namespace cvlm {
@@ -43,7 +45,7 @@ static inline long long align_up(long long v, long long a) { return (v + a - 1) 
 // layout of the saved-activation region of the training forward (encoder.cu: plan_saved)
 struct Saved {
     long long off_x0b, off_php, off_t, off_gall, off_gpre, off_n1, off_n2, off_blocks, block_stride;
-    long long b_xb, b_rows1, b_qkv, b_o, b_xh2, b_rstd2, b_hpre;     // offsets inside one block's slot
+    long long b_xb, b_rows1, b_qkv, b_o, b_xh2, b_rstd2, b_hpre, b_lse;     // offsets inside one block's slot
     long long total;
 };
 Saved plan_saved(const cvlm_encoder_config& c, int batch);

@@ -207,8 +207,10 @@ int backward_impl(cvlm_encoder* enc, int batch, const float* dout_nhwc, const fl
         }
         f.launches += 1;     // two launches, one counted by run()
         CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
-            return attention_backward_launch(blk_ptr(i, sv.b_qkv), blk_ptr(i, sv.b_o), dob, big, lse, dsum, relh, relw, batch,
-                                             g, window, c.num_heads, hd, stream);
+            const bool ready = enc->lse_saved[i] != 0;
+            float* lse_i = ready ? reinterpret_cast<float*>(const_cast<char*>(blk_ptr(i, sv.b_lse))) : lse;
+            return attention_backward_launch(blk_ptr(i, sv.b_qkv), blk_ptr(i, sv.b_o), dob, big, lse_i, dsum, relh, relw,
+                                             batch, g, window, c.num_heads, hd, stream, ready);
         }));
         {   // du * gamma1 = dqkv (Wqkv gamma1)
             GemmArgs ga;
@@ -307,6 +309,23 @@ int cvlm_op_attention_backward(const void* qkv, const void* o, const void* dout,
                                int heads, int head_dim, cvlm_stream_t stream) {
     return attention_backward_launch(qkv, o, dout, dqkv, lse, dsum, rel_pos_h, rel_pos_w, batch, grid_side, window, heads,
                                      head_dim, static_cast<cudaStream_t>(stream));
+}
+
+int cvlm_op_attention_lse(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
+                          int grid_side, int window, int heads, int head_dim, float* lse, cvlm_stream_t stream) {
+    if (!lse) return set_error(CVLM_ERR_ARG, "attention_lse: null lse");
+    bool wrote = false;
+    CVLM_TRY(attention_launch(qkv, out, rel_pos_h, rel_pos_w, batch, grid_side, window, heads, head_dim,
+                              static_cast<cudaStream_t>(stream), lse, &wrote));
+    if (!wrote) return set_error(CVLM_ERR_UNSUPPORTED, "attention_lse: this shape runs on the kernel that does not produce the log-sum-exp");
+    return CVLM_OK;
+}
+
+int cvlm_op_attention_backward_lse(const void* qkv, const void* o, const void* dout, void* dqkv, const float* lse,
+                                   float* dsum, const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side,
+                                   int window, int heads, int head_dim, cvlm_stream_t stream) {
+    return attention_backward_launch(qkv, o, dout, dqkv, const_cast<float*>(lse), dsum, rel_pos_h, rel_pos_w, batch, grid_side,
+                                     window, heads, head_dim, static_cast<cudaStream_t>(stream), true);
 }
 
 int cvlm_op_ln_bwd(int xhat_kind, const float* gin, const float* gamma, const void* xsrc, const float* stat,

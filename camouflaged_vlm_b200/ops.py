@@ -103,6 +103,21 @@ def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tenso
 
 
 @_on_tensor_device
+def attention_lse(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, batch: int, grid: int,
+                  window: int, heads: int, head_dim: int):
+    """``attention`` that also returns every token's row log-sum-exp (fp32 [rows, heads], log2 domain): what the training
+    forward keeps for the backward kernels.  Only for the shapes of the tcgen05 kernels (64 x 64 global, 14 x 14 windows)."""
+    _need_cuda(qkv, rel_pos_h, rel_pos_w)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    out = torch.empty(qkv.shape[0], heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(qkv.shape[0], heads, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.load().cvlm_op_attention_lse(qkv.data_ptr(), out.data_ptr(), rel_pos_h.contiguous().data_ptr(),
+                                                 rel_pos_w.contiguous().data_ptr(), batch, grid, window, heads, head_dim,
+                                                 lse.data_ptr(), _lib.stream_ptr()), "cvlm_op_attention_lse")
+    return out, lse
+
+
+@_on_tensor_device
 def attention_plain(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
     """softmax(q k^T / sqrt(head_dim)) v per image, no relative-position terms; qkv bf16 [batch * tokens, 3 * heads * hd]."""
     _need_cuda(qkv)
@@ -201,14 +216,23 @@ def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> tor
 # ------------------------------------------------------------------ backward-pass kernels (adapter-only training)
 @_on_tensor_device
 def attention_backward(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, rel_pos_h: torch.Tensor,
-                       rel_pos_w: torch.Tensor, batch: int, grid: int, window: int, heads: int, head_dim: int) -> torch.Tensor:
-    """d(loss)/d(qkv) (bf16 [batch*grid^2, 3*D]) of ``attention`` given ``o`` (its output) and ``dout``."""
+                       rel_pos_w: torch.Tensor, batch: int, grid: int, window: int, heads: int, head_dim: int,
+                       lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d(loss)/d(qkv) (bf16 [batch*grid^2, 3*D]) of ``attention`` given ``o`` (its output) and ``dout``.  ``lse`` (from
+    ``attention_lse``) lets the kernels skip their own log-sum-exp sweep."""
     for t in (qkv, o, dout, rel_pos_h, rel_pos_w):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
     rows = batch * grid * grid
     dqkv = torch.zeros_like(qkv)
-    lse = torch.empty(rows, heads, device=qkv.device, dtype=torch.float32)
-    dsum = torch.empty_like(lse)
+    dsum = torch.empty(rows, heads, device=qkv.device, dtype=torch.float32)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.shape == (rows, heads)
+        _lib.check(_lib.load().cvlm_op_attention_backward_lse(qkv.data_ptr(), o.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                                                              lse.data_ptr(), dsum.data_ptr(), rel_pos_h.data_ptr(),
+                                                              rel_pos_w.data_ptr(), batch, grid, window, heads, head_dim,
+                                                              _lib.stream_ptr()), "cvlm_op_attention_backward_lse")
+        return dqkv
+    lse = torch.empty_like(dsum)
     _lib.check(_lib.load().cvlm_op_attention_backward(qkv.data_ptr(), o.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
                                                       lse.data_ptr(), dsum.data_ptr(), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(),
                                                       batch, grid, window, heads, head_dim, _lib.stream_ptr()),

@@ -168,6 +168,16 @@ int cvlm_encoder_backward(cvlm_encoder* enc, int batch, const float* dout_nhwc, 
 int cvlm_op_attention_backward(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
                                const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side, int window,
                                int heads, int head_dim, cvlm_stream_t stream);
+/* cvlm_op_attention that also leaves every token's row log-sum-exp (log2 domain, relative-position terms included) in
+ * lse, fp32 [batch*G*G, heads] -- what the training forward keeps for the backward kernels.  CVLM_ERR_UNSUPPORTED for
+ * shapes that run on the mma.sync fallback kernel, which does not produce it. */
+int cvlm_op_attention_lse(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
+                          int grid_side, int window, int heads, int head_dim, float* lse, cvlm_stream_t stream);
+/* cvlm_op_attention_backward with lse already filled by cvlm_op_attention_lse: the kernels skip their own sweep over
+ * S = q k^T that would compute it. */
+int cvlm_op_attention_backward_lse(const void* qkv, const void* o, const void* dout, void* dqkv, const float* lse,
+                                   float* dsum, const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side,
+                                   int window, int heads, int head_dim, cvlm_stream_t stream);
 /* LayerNorm backward, one warp per row: dx = (residual ? residual : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),
  * g = gin * gamma (gamma NULL: already folded).  xhat_kind 0: xsrc = raw bf16 x, stat = (rstd, -mean*rstd) rows;
  * 1: xsrc = bf16 xhat, stat = rstd rows; 2: xsrc = fp32 x, statistics recomputed with eps.  dxb (optional) = bf16(dx). */

@@ -81,6 +81,49 @@ def test_attention_backward_generic_kernels_on_the_global_grid():
         _lib.set_option("attn_legacy", 0)
 
 
+@pytest.mark.parametrize("batch,grid,window,heads,hd", [(1, 64, 0, 2, 80), (2, 64, 14, 2, 80), (1, 64, 14, 1, 64),
+                                                      (1, 28, 14, 2, 80), (1, 64, 0, 1, 64)])
+def test_attention_backward_with_the_forward_log_sum_exp(batch, grid, window, heads, hd):
+    """The training forward keeps every row's log-sum-exp (written by the tcgen05 attention kernels) so that the backward
+    kernels skip their own sweep over S: same gradients as the self-contained backward, and the saved values equal the
+    ones the backward computes for itself."""
+    from camouflaged_vlm_b200 import _lib
+    D = heads * hd
+    S = window if window > 0 else grid
+    rows = batch * grid * grid
+    qkv = _randn(rows, 3 * D, seed=21, scale=1.0, dtype=torch.bfloat16)
+    relh = _randn(2 * S - 1, hd, seed=22, scale=0.3, dtype=torch.bfloat16)
+    relw = _randn(2 * S - 1, hd, seed=23, scale=0.3, dtype=torch.bfloat16)
+    dout = _randn(rows, D, seed=24, dtype=torch.bfloat16)
+    o, lse = ops.attention_lse(qkv, relh, relw, batch, grid, window, heads, hd)
+    assert torch.equal(o, ops.attention(qkv, relh, relw, batch, grid, window, heads, hd))
+    assert torch.isfinite(lse).all()
+    # the backward's own log-sum-exp (global blocks write it to the scratch)
+    dqkv0 = torch.zeros_like(qkv)
+    lse0 = torch.full((rows, heads), float("nan"), device="cuda")
+    dsum = torch.empty_like(lse0)
+    _lib.check(_lib.load().cvlm_op_attention_backward(qkv.data_ptr(), o.data_ptr(), dout.data_ptr(), dqkv0.data_ptr(),
+                                                      lse0.data_ptr(), dsum.data_ptr(), relh.data_ptr(), relw.data_ptr(),
+                                                      batch, grid, window, heads, hd, _lib.stream_ptr()), "attention_backward")
+    if window == 0:
+        assert (lse - lse0).abs().max().item() < 2e-3          # log2 units; the forward's polynomial exponentials
+    got = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse)
+    torch.cuda.synchronize()
+    assert _rel(got, dqkv0) < 2e-3
+    leaf = qkv.float().requires_grad_(True)
+    (attention_reference(leaf, relh, relw, batch, grid, window, heads, hd) * dout.float()).sum().backward()
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = _rel(got[:, sl], leaf.grad[:, sl])
+        assert err < GRAD_TOL, f"{name}: rel-L2 {err:.3e}"
+
+
+def test_attention_lse_refuses_the_fallback_kernel():
+    qkv = _randn(4 * 16 * 16, 3 * 64, seed=31, dtype=torch.bfloat16)
+    rel = _randn(2 * 16 - 1, 32, seed=32, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.attention_lse(qkv, rel, rel, 4, 16, 0, 2, 32)
+
+
 def _attention_backward_case(batch, grid, window, heads, hd):
     D = heads * hd
     S = window if window > 0 else grid
