@@ -54,6 +54,8 @@ def parse_args():
                          "processed in micro-batches of --batch; 0 = weak scaling (--batch images per GPU per step)")
     ap.add_argument("--gather-dtype", choices=["fp32", "bf16"], default="fp32",
                     help="payload of the N>1 embedding all-gather (bf16 halves the bytes, adds ~1.1e-3 rel-L2)")
+    ap.add_argument("--e2e-chunk", type=int, default=16,
+                    help="images per chunk of the host-buffer call timed as e2e (upload / encoder / download pipeline)")
     return ap.parse_args()
 
 
@@ -442,7 +444,7 @@ def run_ours(args):
         x_host = torch.empty(B, cfg.in_chans, cfg.img_size, cfg.img_size, pin_memory=True)
         x_host.copy_(x_dev)
         out_host = torch.empty(B, cfg.out_chans, cfg.grid, cfg.grid, pin_memory=True)
-        CH = 8
+        CH = max(1, min(args.e2e_chunk, B))
         e2e_gather = [ChunkGatherer(B, tail, dev, gdtype) for _ in range(2)] if world > 1 else None
         e2e_calls = [0]
 

@@ -542,12 +542,14 @@ int cvlm_encoder_forward_host(cvlm_encoder* enc, const float* images_host, int b
     }
     cudaEvent_t ready[2] = {enc->host_events[0], enc->host_events[1]}, freed[2] = {enc->host_events[2], enc->host_events[3]};
     cudaEvent_t edge = enc->host_events[4];
-    CVLM_CUDA(cudaEventRecord(edge, main));                 // the copy stream starts after what is already queued
-    CVLM_CUDA(cudaStreamWaitEvent(cs, edge, 0));
+    // The copy stream does NOT wait for what is already queued on `stream`: a staging half only has to be free, i.e. the
+    // encoder that last read it must have run (freed[], kept across calls; waiting on a never-recorded event is a no-op).
+    // Back-to-back calls therefore upload their first chunk underneath the previous call's last encoder.  images_host must
+    // be complete when the call is made (it is host memory: no stream orders it).
     const int n_chunks = (batch + chunk - 1) / chunk;
     auto upload = [&](int i) -> int {
         const int s = i * chunk, e = s + chunk < batch ? s + chunk : batch;
-        if (i >= 2) CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));
+        CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));
         CVLM_CUDA(cudaMemcpyAsync(stage_dev + static_cast<long long>(i & 1) * chunk * img_elems, images_host + s * img_elems,
                                   static_cast<size_t>(e - s) * img_elems * 4, cudaMemcpyHostToDevice, cs));
         CVLM_CUDA(cudaEventRecord(ready[i & 1], cs));
@@ -567,9 +569,12 @@ int cvlm_encoder_forward_host(cvlm_encoder* enc, const float* images_host, int b
                               workspace_bytes, nullptr, 0, main));
         launches += enc->last_launches;
         CVLM_CUDA(cudaEventRecord(freed[i & 1], main));
-        CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));      // this chunk's embeddings leave under the next chunk's encoder
+        // this chunk's embeddings leave under the next chunk's encoder; the last chunk's go out on `stream` itself, so that
+        // the copy stream is idle again while the last encoder runs (the next call's first upload goes there)
+        cudaStream_t ds = i + 1 < n_chunks ? cs : main;
+        if (ds == cs) CVLM_CUDA(cudaStreamWaitEvent(cs, freed[i & 1], 0));
         CVLM_CUDA(cudaMemcpyAsync(out_host + s * emb_elems, emb_dev + s * emb_elems, static_cast<size_t>(e - s) * emb_elems * 4,
-                                  cudaMemcpyDeviceToHost, cs));
+                                  cudaMemcpyDeviceToHost, ds));
     }
     CVLM_CUDA(cudaEventRecord(edge, cs));
     CVLM_CUDA(cudaStreamWaitEvent(main, edge, 0));          // out_host is valid once `stream` has been synchronised

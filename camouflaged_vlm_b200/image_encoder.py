@@ -369,7 +369,7 @@ class ImageEncoderViT(nn.Module):
         self.last_launch_count = launches
 
     @torch.no_grad()
-    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunk: int = 8,
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, chunk: int = 16,
                      interm: bool = False, return_device: bool = False, on_chunk=None):
         """Embeddings for a batch that lives in HOST memory (``x_host`` fp32 [B,3,S,S], ideally pinned): the batch is
         cut into chunks of ``chunk`` images; the host->device copy of chunk i+1 and the device->host copy of the

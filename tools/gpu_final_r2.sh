@@ -36,7 +36,7 @@ KREG='regex:gemm_bf16_tcgen05_kernel|attention_kernel|attn_global_tc2_kernel|att
 BENCH="python bench.py --steps 1 --warmup 3 --batch 32 --skip-cpu-baseline --skip-e2e --skip-decoder --skip-train"
 echo "=== ncu launch list of one bench step" | tee -a $L
 $BENCH > $O/plain_$TAG.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 729 -c 243 --csv \
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 726 -c 242 --csv \
     --log-file $O/ncu_launches_${TAG}_b32.csv $BENCH > $O/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?" | tee -a $L
 echo "=== ncu full: qkv / proj / lin1 / lin2 of one block" | tee -a $L
