@@ -397,14 +397,17 @@ class ImageEncoderViT(nn.Module):
             self._stage = torch.empty((2,) + shape, device=dev, dtype=torch.float32)     # two staging buffers, back to back
         stage = [self._stage[0], self._stage[1]]
         ready = [torch.cuda.Event() for _ in range(2)]        # staging buffer filled
-        free = [torch.cuda.Event() for _ in range(2)]         # staging buffer consumed by the encoder
+        # staging buffer consumed by the encoder: kept across calls (like the C entry point), so that the copy stream only
+        # waits for the reader of the half it is about to overwrite and back-to-back calls overlap
+        if getattr(self, "_stage_free", None) is None or self._stage_free[0] is not self._stage:
+            self._stage_free = (self._stage, [torch.cuda.Event() for _ in range(2)], [False, False])
+        free, free_recorded = self._stage_free[1], self._stage_free[2]
         spans = [(s, min(B, s + chunk)) for s in range(0, B, chunk)]
-        cs.wait_stream(main)
 
         def upload(i):
             s, e = spans[i]
             with torch.cuda.stream(cs):
-                if i >= 2:
+                if free_recorded[i % 2]:
                     cs.wait_event(free[i % 2])
                 stage[i % 2][:e - s].copy_(x_host[s:e], non_blocking=True)
                 ready[i % 2].record(cs)
@@ -439,11 +442,15 @@ class ImageEncoderViT(nn.Module):
             main.wait_event(ready[i % 2])
             self._run(stage[i % 2][:e - s], emb[s:e], [t[s:e] for t in interms])
             free[i % 2].record(main)
+            free_recorded[i % 2] = True
             if on_chunk is not None:
                 on_chunk(s, e, emb[s:e])
-            with torch.cuda.stream(cs):             # this chunk's embeddings go out under the next chunk's encoder
-                cs.wait_event(free[i % 2])
-                out_host[s:e].copy_(emb[s:e], non_blocking=True)
+            if i + 1 < len(spans):
+                with torch.cuda.stream(cs):         # this chunk's embeddings go out under the next chunk's encoder
+                    cs.wait_event(free[i % 2])
+                    out_host[s:e].copy_(emb[s:e], non_blocking=True)
+            else:                                   # the last ones on the compute stream: the copy stream stays free
+                out_host[s:e].copy_(emb[s:e], non_blocking=True)   # for the next call's first upload
         main.wait_stream(cs)
         ret = [out_host]
         if return_device:
