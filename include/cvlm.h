@@ -112,7 +112,10 @@ int cvlm_encoder_forward_partial(cvlm_encoder* enc, const float* images, const f
  * pinned.  The batch is cut into chunks of `chunk` images: the upload of chunk i+1 and the download of the embeddings of
  * chunk i-1 run on `copy_stream` underneath the encoder of chunk i on `stream` (stage_dev: device, 2*chunk*3*S*S floats;
  * emb_dev: device, [batch,out,g,g]; interm_dev: NULL or one device pointer [batch,g,g,D] per global block; workspace for
- * `chunk` images).  Stream-ordered only: out_host is valid once `stream` has been synchronised. */
+ * `chunk` images).  Stream-ordered only: out_host is valid once `stream` has been synchronised.  Back-to-back calls on the
+ * same handle, streams and stage_dev overlap: the first upload of a call runs underneath the last encoder of the previous
+ * one (a staging half waits only for the encoder that last read it), so images_host must be complete when the call is made
+ * -- it is host memory, no stream orders it -- and stay untouched until `copy_stream` has consumed it. */
 int cvlm_encoder_forward_host(cvlm_encoder* enc, const float* images_host, int batch, int chunk, float* out_host,
                               float* emb_dev, float* const* interm_dev, float* stage_dev, void* workspace,
                               long long workspace_bytes, cvlm_stream_t copy_stream, cvlm_stream_t stream);
