@@ -400,8 +400,10 @@ static int launch_attention(const AttnParams& p, int batch, cudaStream_t stream)
 }
 
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
-                     int window, int heads, int head_dim, cudaStream_t stream, float* lse_out, bool* lse_written) {
+                     int window, int heads, int head_dim, cudaStream_t stream, float* lse_out, bool* lse_written,
+                     float* tw_out, float* th_out, bool* tabs_written) {
     if (lse_written) *lse_written = false;
+    if (tabs_written) *tabs_written = false;
     if (!qkv || !out || !relh || !relw) return set_error(CVLM_ERR_ARG, "attention: null pointer");
     if (batch <= 0 || grid_side <= 0 || heads <= 0) return set_error(CVLM_ERR_ARG, "attention: bad sizes");
     if (head_dim != 32 && head_dim != 64 && head_dim != 80)
@@ -426,7 +428,8 @@ int attention_launch(const void* qkv, void* out, const void* relh, const void* r
     const bool legacy = option(OPT_ATTN_LEGACY) != 0;
     if (!legacy && p.S == 64 && p.G == 64 && (head_dim == 64 || head_dim == 80)) {
         if (lse_written) *lse_written = lse_out != nullptr;
-        return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream, lse_out);
+        if (tabs_written) *tabs_written = tw_out != nullptr && th_out != nullptr;
+        return attention_global_tc2_launch(qkv, out, relh, relw, batch, heads, head_dim, stream, lse_out, tw_out, th_out);
     }
     if (!legacy && window == 14 && (head_dim == 64 || head_dim == 80)) {
         if (lse_written) *lse_written = lse_out != nullptr;

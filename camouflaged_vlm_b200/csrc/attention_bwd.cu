@@ -44,6 +44,11 @@ struct BwdParams {
     int G, S, nW, heads, D, TWP, TWK;
     float scale, scale_log2;
     int lse_ready;              // lse was written by the forward kernel: the specialised kernels skip their own S sweep for it
+    // 64 x 64 global blocks, written by the training forward (attention_tc2.cu), log2 domain, fp32 [B*G*G, heads, 64] each:
+    // tw_tab[q][kx] = T_w[q][qx - kx + 63] and th_tab[q][ky] = T_h[q][qy - ky + 63]; NULL: the kernels project q on the
+    // rel-pos tables themselves
+    const float* tw_tab;
+    const float* th_tab;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -709,6 +714,11 @@ struct Bwd64Smem {
     static constexpr int dkv_off_rh = dkv_off_rw + 128 * HDP * 2, dkv_off_tw = dkv_off_rh + 16 * HDP * 2;
     static constexpr int dkv_off_row = dkv_off_tw + TW, dkv_total = dkv_off_row + 3 * BW_T * 4;
     static_assert(192 * HDP * 2 + BW_T * HDP * 2 <= KV, "tables + dQ staging must fit the K/V double buffer");
+    // dkv with the forward's T tables (attn_bwd_dkv64t): K | V, then two stages of { Q | dO, T_w tile [64][68] fp32, lse | D | T_h }
+    static constexpr int TWT = BW_T * 68 * 4;
+    static constexpr int dkvt_stage = QO + TWT + 3 * BW_T * 4;
+    static constexpr int dkvt_off_st = 2 * BW_T * HDP * 2, dkvt_total = dkvt_off_st + 2 * dkvt_stage;
+    static_assert(2 * (dkvt_total + 1024) <= 233472, "two CTAs of attn_bwd_dkv64t per SM");
 };
 
 template <int HD>
@@ -1263,6 +1273,172 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64_kernel(const Bwd
     }
 }
 
+// dK / dV of the 64 x 64 global blocks with the forward's T tables (BwdParams::tw_tab / th_tab): nothing is projected on the
+// rel-pos tables here (that was a third of the kernel's MMAs), and the query tiles are double-buffered: the loads of
+// tile qt + 1 (Q, dO, the [64][64] T_w tile, lse, D, the T_h column) run under the MMAs of tile qt.
+template <int HD>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64t_kernel(const BwdParams p) {
+    using Plan = Bwd64Smem<HD>;
+    constexpr int HDP = Plan::HDP, KSTEPS = HD / 16, DT = HD / 8, CH = HD / 8, TWS = 68;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+    __nv_bfloat16* sV = sK + BW_T * HDP;
+    auto stQ = [&](int st) { return reinterpret_cast<__nv_bfloat16*>(smem + Plan::dkvt_off_st + st * Plan::dkvt_stage); };
+    auto stTw = [&](int st) { return reinterpret_cast<float*>(smem + Plan::dkvt_off_st + st * Plan::dkvt_stage + Plan::QO); };
+    auto stRow = [&](int st) { return stTw(st) + BW_T * TWS; };      // lse[64] | D[64] | T_h column[64]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int kt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const long long tok_base = static_cast<long long>(b) * 4096;
+    const int ld = 3 * p.D;
+    const __nv_bfloat16* qbase = p.qkv + head * HD;
+    const __nv_bfloat16* kbase = qbase + p.D;
+    const __nv_bfloat16* vbase = qbase + 2 * p.D;
+
+    auto load_tile = [&](int qt, int st) {
+        __nv_bfloat16* sQ = stQ(st);
+        __nv_bfloat16* sdO = sQ + BW_T * HDP;
+        for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+            const int r = i / CH, c = i - r * CH;
+            const long long tok = tok_base + qt * 64 + r;
+            cp_async_16(smem_u32(sQ + r * HDP + c * 8), qbase + tok * ld + c * 8, true);
+            cp_async_16(smem_u32(sdO + r * HDP + c * 8), p.dout + tok * p.D + head * HD + c * 8, true);
+        }
+        float* sTw = stTw(st);
+        for (int i = tid; i < BW_T * 16; i += BW_THREADS) {
+            const int r = i >> 4, c = i & 15;
+            const long long row = (tok_base + qt * 64 + r) * p.heads + head;
+            cp_async_16(smem_u32(sTw + r * TWS + c * 4), p.tw_tab + row * 64 + c * 4, true);
+        }
+        if (tid < BW_T) {
+            float* sRow = stRow(st);
+            const long long row = (tok_base + qt * 64 + tid) * p.heads + head;
+            cp_async_4(smem_u32(sRow + tid), p.lse + row);
+            cp_async_4(smem_u32(sRow + BW_T + tid), p.dsum + row);
+            cp_async_4(smem_u32(sRow + 2 * BW_T + tid), p.th_tab + row * 64 + kt);
+        }
+    };
+
+    for (int i = tid; i < BW_T * CH; i += BW_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const long long row = (tok_base + kt * 64 + r) * ld + c * 8;
+        cp_async_16(smem_u32(sK + r * HDP + c * 8), kbase + row, true);
+        cp_async_16(smem_u32(sV + r * HDP + c * 8), vbase + row, true);
+    }
+    load_tile(0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t kf[KSTEPS][4], vf[KSTEPS][4];
+    {
+        const int row = warp * 16 + (lane & 15);
+        const int koff = (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            ldmatrix_x4(smem_u32(sK + row * HDP + ks * 16 + koff), kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3]);
+            ldmatrix_x4(smem_u32(sV + row * HDP + ks * 16 + koff), vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3]);
+        }
+    }
+    const int kx0 = warp * 16 + g, kx1 = kx0 + 8;               // this thread's two key rows = kx
+    float dk[DT][4], dv[DT][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    const int krow = (lane & 7) + ((lane >> 4) << 3);
+    const int kcol = ((lane >> 3) & 1) * 8;
+
+    for (int qt = 0; qt < 64; ++qt) {
+        const int st = qt & 1;
+        // (tile qt is resident: the prologue / the previous iteration waited for it; every warp has left tile qt - 1)
+        if (qt + 1 < 64) load_tile(qt + 1, st ^ 1);
+        cp_async_commit();
+        const __nv_bfloat16* sQ = stQ(st);
+        const __nv_bfloat16* sdO = sQ + BW_T * HDP;
+        const float* sTw = stTw(st);
+        const float* sLse = stRow(st);
+        const float* sD = sLse + BW_T;
+        const float* sThc = sD + BW_T;
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(smem_u32(sQ + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(s[2 * np], kf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], kf[ks], b2, b3);
+                ldmatrix_x4(smem_u32(sdO + (np * 16 + krow) * HDP + ks * 16 + kcol), b0, b1, b2, b3);
+                mma_bf16_16816(dp[2 * np], vf[ks], b0, b1);
+                mma_bf16_16816(dp[2 * np + 1], vf[ks], b2, b3);
+            }
+        }
+        uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float pv[4], dsv[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = nt * 8 + 2 * t + e;             // query column = qx
+                const float c = sThc[q] - sLse[q], dd = sD[q];
+                const float* tw = sTw + q * TWS;              // bank = (4 q + kx) mod 32: distinct over the warp
+                const float l0 = fmaf(s[nt][e], p.scale_log2, c + tw[kx0]);
+                const float l1 = fmaf(s[nt][2 + e], p.scale_log2, c + tw[kx1]);
+                pv[e] = ex2f(l0);
+                pv[2 + e] = ex2f(l1);
+                dsv[e] = pv[e] * (dp[nt][e] - dd);
+                dsv[2 + e] = pv[2 + e] * (dp[nt][2 + e] - dd);
+            }
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+            dsf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(dsv[0], dsv[1]);
+            dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+        }
+        {
+            const int vrow = lane & 15;
+            const int vcol = (lane >> 4) * 8;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int dpi = 0; dpi < DT / 2; ++dpi) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(smem_u32(sdO + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dv[2 * dpi], pf[kk], b0, b1);
+                    mma_bf16_16816(dv[2 * dpi + 1], pf[kk], b2, b3);
+                    ldmatrix_x4_trans(smem_u32(sQ + (kk * 16 + vrow) * HDP + dpi * 16 + vcol), b0, b1, b2, b3);
+                    mma_bf16_16816(dk[2 * dpi], dsf[kk], b0, b1);
+                    mma_bf16_16816(dk[2 * dpi + 1], dsf[kk], b2, b3);
+                }
+            }
+        }
+        cp_async_wait<0>();                                  // tile qt + 1 has landed (this thread's part)
+        __syncthreads();                                     // ... everybody's; and everybody has left tile qt
+    }
+    __nv_bfloat16* oK = sK + warp * 16 * HDP;
+    __nv_bfloat16* oV = sV + warp * 16 * HDP;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        *reinterpret_cast<uint32_t*>(oK + g * HDP + i * 8 + 2 * t) = pack_bf16(dk[i][0] * p.scale, dk[i][1] * p.scale);
+        *reinterpret_cast<uint32_t*>(oK + (g + 8) * HDP + i * 8 + 2 * t) = pack_bf16(dk[i][2] * p.scale, dk[i][3] * p.scale);
+        *reinterpret_cast<uint32_t*>(oV + g * HDP + i * 8 + 2 * t) = pack_bf16(dv[i][0], dv[i][1]);
+        *reinterpret_cast<uint32_t*>(oV + (g + 8) * HDP + i * 8 + 2 * t) = pack_bf16(dv[i][2], dv[i][3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i - r * CH;
+        __nv_bfloat16* dst = p.dqkv + (tok_base + kt * 64 + warp * 16 + r) * ld + head * HD + c * 8;
+        *reinterpret_cast<uint4*>(dst + p.D) = *reinterpret_cast<const uint4*>(oK + r * HDP + c * 8);
+        *reinterpret_cast<uint4*>(dst + 2 * p.D) = *reinterpret_cast<const uint4*>(oV + r * HDP + c * 8);
+    }
+}
+
 // ================================================================================================
 // 14 x 14 windows: one CTA per (window, head) with everything resident.  The generic pair above cuts the 196 tokens of
 // a window into 4 x 4 tiles of 64 (the fourth holds 4 rows) and launches 25 600 small CTAs per block, each a chain of
@@ -1678,8 +1854,14 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
         CVLM_TRY(ensure_dynamic_smem(attn_bwd_dq64_kernel<HD>, Bwd64Smem<HD>::dq_total, g0));
         attn_bwd_dq64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dq_total, stream>>>(p);
         CVLM_CUDA(cudaGetLastError());
-        CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64_kernel<HD>, Bwd64Smem<HD>::dkv_total, g1));
-        attn_bwd_dkv64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dkv_total, stream>>>(p);
+        if (p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready) {
+            static unsigned char g2[kMaxDevices] = {};
+            CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64t_kernel<HD>, Bwd64Smem<HD>::dkvt_total, g2));
+            attn_bwd_dkv64t_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dkvt_total, stream>>>(p);
+        } else {
+            CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64_kernel<HD>, Bwd64Smem<HD>::dkv_total, g1));
+            attn_bwd_dkv64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dkv_total, stream>>>(p);
+        }
         CVLM_CUDA(cudaGetLastError());
         return CVLM_OK;
     }
@@ -1718,7 +1900,7 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
 // Every element of dqkv that belongs to a token of the grid is written (2 launches).
 int attention_backward_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
                               const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
-                              int head_dim, cudaStream_t stream, bool lse_ready) {
+                              int head_dim, cudaStream_t stream, bool lse_ready, const float* tw_tab, const float* th_tab) {
     if (!qkv || !o || !dout || !dqkv || !lse || !dsum || !relh || !relw)
         return set_error(CVLM_ERR_ARG, "attention_backward: null pointer");
     if (batch <= 0 || grid_side <= 0 || heads <= 0) return set_error(CVLM_ERR_ARG, "attention_backward: bad sizes");
@@ -1729,6 +1911,8 @@ int attention_backward_launch(const void* qkv, const void* o, const void* dout, 
     p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
     p.lse = lse;
     p.lse_ready = lse_ready ? 1 : 0;
+    p.tw_tab = tw_tab;
+    p.th_tab = th_tab;
     p.dsum = dsum;
     p.relh = static_cast<const __nv_bfloat16*>(relh);
     p.relw = static_cast<const __nv_bfloat16*>(relw);

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
 attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmRelH, const __grid_constant__ CUtensorMap tmRelW,
                        __nv_bfloat16* __restrict__ out, int heads, int D, float scale_log2, int L,
-                       float* __restrict__ lse_out) {
+                       float* __restrict__ lse_out, float* __restrict__ tw_out, float* __restrict__ th_out) {
     constexpr bool HI = HD > 64;
     constexpr uint32_t Q_BYTES = (HI ? 2 : 1) * G2_QTILE;
     constexpr uint32_t KV_BYTES = (HI ? 2 : 1) * G2_KTILE;
@@ -431,6 +431,25 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // training forward: the row's log-sum-exp (log2 domain, rel-pos terms included) for the backward kernels
         if (lse_out != nullptr && live)
             lse_out[(static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head] = m_used + log2f(l);
+        if (!PLAIN && tw_out != nullptr && th_out != nullptr) {
+            // ... and this row's rel-pos terms as the dK / dV kernel wants them (it walks the queries as columns and cannot
+            // project them itself without a third of its MMAs): tw[kx] = T_w[q][qx - kx + 63], th[ky] = T_h[q][qy - ky + 63]
+            const long long row = (static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head;
+            float4* twp = reinterpret_cast<float4*>(tw_out + row * 64);
+            float4* thp = reinterpret_cast<float4*>(th_out + row * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float a0, a1, a2, a3;
+                f32x2_unpack(tw2[2 * i], a0, a1);
+                f32x2_unpack(tw2[2 * i + 1], a2, a3);
+                twp[i] = make_float4(a0, a1, a2, a3);
+            }
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int o = 128 + 2 * t + qrow + 63 - 4 * i;       // ky = 4 i .. 4 i + 3
+                thp[i] = make_float4(trow[PLAIN ? 0 : o], trow[PLAIN ? 0 : o - 1], trow[PLAIN ? 0 : o - 2], trow[PLAIN ? 0 : o - 3]);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             tmem_ld_32x32(t_o + c * 32, va);
@@ -472,7 +491,8 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 template <int HD, int POLY, bool PLAIN>
 static int launch_global_tc2(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                             int tokens, cudaStream_t stream, float* lse_out = nullptr) {
+                             int tokens, cudaStream_t stream, float* lse_out = nullptr, float* tw_out = nullptr,
+                             float* th_out = nullptr) {
     const int D = heads * HD;
     CUtensorMap tq, tkv, th, tw;
     MapSpec s = map_spec_zero();
@@ -514,20 +534,20 @@ static int launch_global_tc2(const void* qkv, void* out, const void* relh, const
     CVLM_TRY(ensure_dynamic_smem(kern, G2_SMEM, ready));
     dim3 grid((tokens + 255) / 256, heads, batch);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * kLog2eG2;
-    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens, lse_out);
+    kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tq, tkv, th, tw, static_cast<__nv_bfloat16*>(out), heads, D, scale_log2, tokens, lse_out, tw_out, th_out);
     CVLM_CUDA(cudaGetLastError());
     return CVLM_OK;
 }
 
 template <int HD>
 static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const void* relh, const void* relw, int batch,
-                                  int heads, cudaStream_t stream, float* lse_out) {
+                                  int heads, cudaStream_t stream, float* lse_out, float* tw_out, float* th_out) {
     switch (poly) {
-        case 0: return launch_global_tc2<HD, 0, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
-        case 2: return launch_global_tc2<HD, 2, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
-        case 4: return launch_global_tc2<HD, 4, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
-        case 6: return launch_global_tc2<HD, 6, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
-        case 8: return launch_global_tc2<HD, 8, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out);
+        case 0: return launch_global_tc2<HD, 0, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out, tw_out, th_out);
+        case 2: return launch_global_tc2<HD, 2, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out, tw_out, th_out);
+        case 4: return launch_global_tc2<HD, 4, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out, tw_out, th_out);
+        case 6: return launch_global_tc2<HD, 6, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out, tw_out, th_out);
+        case 8: return launch_global_tc2<HD, 8, false>(qkv, out, relh, relw, batch, heads, 4096, stream, lse_out, tw_out, th_out);
         default: return set_error(CVLM_ERR_ARG, "CVLM_ATTN_POLY must be 0, 2, 4, 6 or 8");
     }
 }
@@ -535,11 +555,11 @@ static int launch_global_tc2_poly(int poly, const void* qkv, void* out, const vo
 // Global attention over a 64x64 token grid, head_dim 64 or 80.
 // CVLM_ATTN_POLY = how many of every 16 exponential pairs run on the FMA pipe (tuning knob; default below).
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                                int head_dim, cudaStream_t stream, float* lse_out) {
+                                int head_dim, cudaStream_t stream, float* lse_out, float* tw_out, float* th_out) {
     if (batch > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "attention: batch exceeds grid.z; split the batch");
     const int poly = option(OPT_ATTN_POLY);               // cvlm_set_option("attn_poly", n); default 4
-    if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out);
-    if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out);
+    if (head_dim == 80) return launch_global_tc2_poly<80>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out, tw_out, th_out);
+    if (head_dim == 64) return launch_global_tc2_poly<64>(poly, qkv, out, relh, relw, batch, heads, stream, lse_out, tw_out, th_out);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_tc2: head_dim %d", head_dim);
 }
 

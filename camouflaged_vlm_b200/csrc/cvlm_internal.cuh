@@ -102,12 +102,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 // ---- attention (attention.cu)
 // lse_out (optional, training forward): fp32 [batch * grid^2, heads], every token's row log-sum-exp in the log2 domain;
 // *lse_written tells whether the kernel that ran produces it (the tcgen05 kernels do, the mma.sync fallback does not).
+// tw_out / th_out (optional, 64 x 64 global blocks only; *tabs_written): fp32 [batch * grid^2, heads, 64] each, every
+// query's rel-pos terms laid out for the dK / dV kernel (BwdParams::tw_tab / th_tab).
 int attention_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int grid_side,
                      int window, int heads, int head_dim, cudaStream_t stream, float* lse_out = nullptr,
-                     bool* lse_written = nullptr);
+                     bool* lse_written = nullptr, float* tw_out = nullptr, float* th_out = nullptr,
+                     bool* tabs_written = nullptr);
 
 int attention_global_tc2_launch(const void* qkv, void* out, const void* relh, const void* relw, int batch, int heads,
-                                int head_dim, cudaStream_t stream, float* lse_out = nullptr);
+                                int head_dim, cudaStream_t stream, float* lse_out = nullptr, float* tw_out = nullptr,
+                                float* th_out = nullptr);
 
 int attention_plain_tc2_launch(const void* qkv, void* out, int batch, int tokens, int heads, int head_dim,
                                cudaStream_t stream);
@@ -120,7 +124,8 @@ int attention_window_tc2_launch(const void* qkv, void* out, const void* relh, co
 // own sweep over S that would compute it.
 int attention_backward_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* lse, float* dsum,
                               const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
-                              int head_dim, cudaStream_t stream, bool lse_ready = false);
+                              int head_dim, cudaStream_t stream, bool lse_ready = false, const float* tw_tab = nullptr,
+                              const float* th_tab = nullptr);
 int layernorm_train_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, void* xhat_bf16,
                            float* rstd, long long rows, int cols, float eps, cudaStream_t stream);
 int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void* xsrc, const float* stat,

@@ -136,7 +136,12 @@ Saved plan_saved(const cvlm_encoder_config& c, int batch) {
     s.b_hpre = take(M * c.mlp_dim * 2);
     s.b_lse = take(M * c.num_heads * 4);
     s.block_stride = off;
-    s.total = s.off_blocks + s.block_stride * c.depth;
+    s.off_gtab = s.off_blocks + s.block_stride * c.depth;
+    s.gtab_half = align_up(M * c.num_heads * 64 * 4, 1024);
+    s.gtab_stride = 2 * s.gtab_half;
+    int n_global = 0;
+    for (int i = 0; i < c.depth; ++i) n_global += (c.is_global[i] || c.window_size <= 0) ? 1 : 0;
+    s.total = s.off_gtab + s.gtab_stride * n_global;
     return s;
 }
 
@@ -293,6 +298,8 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
         const int window = c.is_global[i] ? 0 : c.window_size;
         const int S = window > 0 ? window : g;
         const long long relb = 2LL * (2 * S - 1) * hd;
+        int global_idx = 0;                  // this block's index among the global blocks (saved-table slot)
+        for (int j = 0; j < i; ++j) global_idx += (c.is_global[j] || c.window_size <= 0) ? 1 : 0;
         const void *qkv_w, *qkv_b, *qkv_c, *relh, *relw, *proj_w, *proj_b, *ln2w, *ln2b, *l1w, *l1b, *l2w, *l2b,
             *l2bf = nullptr;
         CVLM_TRY(f.getb(i, "qkv.w", 2LL * 3 * D * D, &qkv_w));
@@ -323,10 +330,17 @@ int forward_impl(cvlm_encoder* enc, const float* images, const float* highpass, 
         CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
             if (!train) return attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream);
             // the backward kernels need every row's log-sum-exp: the tcgen05 kernels leave it next to the activations
-            bool wrote = false;
+            bool wrote = false, tabs = false;
+            float* tw_tab = nullptr;
+            float* th_tab = nullptr;
+            if (window == 0) {
+                tw_tab = reinterpret_cast<float*>(svb + sv.off_gtab + sv.gtab_stride * global_idx);
+                th_tab = reinterpret_cast<float*>(svb + sv.off_gtab + sv.gtab_stride * global_idx + sv.gtab_half);
+            }
             const int rc = attention_launch(qkv_buf, attn_out, relh, relw, batch, g, window, c.num_heads, hd, stream,
-                                            reinterpret_cast<float*>(blk_ptr(i, sv.b_lse)), &wrote);
+                                            reinterpret_cast<float*>(blk_ptr(i, sv.b_lse)), &wrote, tw_tab, th_tab, &tabs);
             enc->lse_saved[i] = wrote ? 1 : 0;
+            enc->tabs_saved[i] = tabs ? 1 : 0;
             return rc;
         }));
         {   // proj (:502) + shortcut (:443); bias = b_proj + W_proj * b_v

@@ -30,6 +30,7 @@ struct cvlm_encoder {
     std::vector<cudaEvent_t> host_events;   // cvlm_encoder_forward_host: staging-buffer ready / consumed, stream edges
     // training forward: block i's attention kernel left the row log-sum-exp in the saved region (the tcgen05 kernels do)
     unsigned char lse_saved[CVLM_MAX_DEPTH] = {};
+    unsigned char tabs_saved[CVLM_MAX_DEPTH] = {};   // ... and (global blocks) the per-query rel-pos terms for the dK / dV kernel
 };
 
 namespace cvlm {
@@ -46,6 +47,8 @@ static inline long long align_up(long long v, long long a) { return (v + a - 1) 
 struct Saved {
     long long off_x0b, off_php, off_t, off_gall, off_gpre, off_n1, off_n2, off_blocks, block_stride;
     long long b_xb, b_rows1, b_qkv, b_o, b_xh2, b_rstd2, b_hpre, b_lse;     // offsets inside one block's slot
+    // per GLOBAL block (index among the global blocks): tw | th tables, fp32 [M, heads, 64] each (attention_tc2.cu)
+    long long off_gtab, gtab_stride, gtab_half;
     long long total;
 };
 Saved plan_saved(const cvlm_encoder_config& c, int batch);

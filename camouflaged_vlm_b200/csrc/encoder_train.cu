@@ -209,8 +209,16 @@ int backward_impl(cvlm_encoder* enc, int batch, const float* dout_nhwc, const fl
         CVLM_TRY(f.run(window > 0 ? K_ATTN_WINDOW : K_ATTN_GLOBAL, [&] {
             const bool ready = enc->lse_saved[i] != 0;
             float* lse_i = ready ? reinterpret_cast<float*>(const_cast<char*>(blk_ptr(i, sv.b_lse))) : lse;
+            const float* tw_tab = nullptr;
+            const float* th_tab = nullptr;
+            if (ready && enc->tabs_saved[i]) {
+                int gi = 0;                              // this block's slot among the global blocks
+                for (int j = 0; j < i; ++j) gi += (c.is_global[j] || c.window_size <= 0) ? 1 : 0;
+                tw_tab = reinterpret_cast<const float*>(svb + sv.off_gtab + sv.gtab_stride * gi);
+                th_tab = reinterpret_cast<const float*>(svb + sv.off_gtab + sv.gtab_stride * gi + sv.gtab_half);
+            }
             return attention_backward_launch(blk_ptr(i, sv.b_qkv), blk_ptr(i, sv.b_o), dob, big, lse_i, dsum, relh, relw,
-                                             batch, g, window, c.num_heads, hd, stream, ready);
+                                             batch, g, window, c.num_heads, hd, stream, ready, tw_tab, th_tab);
         }));
         {   // du * gamma1 = dqkv (Wqkv gamma1)
             GemmArgs ga;
@@ -312,20 +320,24 @@ int cvlm_op_attention_backward(const void* qkv, const void* o, const void* dout,
 }
 
 int cvlm_op_attention_lse(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
-                          int grid_side, int window, int heads, int head_dim, float* lse, cvlm_stream_t stream) {
+                          int grid_side, int window, int heads, int head_dim, float* lse, float* tw_tab, float* th_tab,
+                          cvlm_stream_t stream) {
     if (!lse) return set_error(CVLM_ERR_ARG, "attention_lse: null lse");
-    bool wrote = false;
+    if ((tw_tab == nullptr) != (th_tab == nullptr)) return set_error(CVLM_ERR_ARG, "attention_lse: tw_tab and th_tab go together");
+    bool wrote = false, tabs = false;
     CVLM_TRY(attention_launch(qkv, out, rel_pos_h, rel_pos_w, batch, grid_side, window, heads, head_dim,
-                              static_cast<cudaStream_t>(stream), lse, &wrote));
+                              static_cast<cudaStream_t>(stream), lse, &wrote, tw_tab, th_tab, &tabs));
     if (!wrote) return set_error(CVLM_ERR_UNSUPPORTED, "attention_lse: this shape runs on the kernel that does not produce the log-sum-exp");
+    if (tw_tab && !tabs) return set_error(CVLM_ERR_UNSUPPORTED, "attention_lse: the rel-pos tables are written for 64 x 64 global blocks only");
     return CVLM_OK;
 }
 
 int cvlm_op_attention_backward_lse(const void* qkv, const void* o, const void* dout, void* dqkv, const float* lse,
                                    float* dsum, const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side,
-                                   int window, int heads, int head_dim, cvlm_stream_t stream) {
+                                   int window, int heads, int head_dim, const float* tw_tab, const float* th_tab,
+                                   cvlm_stream_t stream) {
     return attention_backward_launch(qkv, o, dout, dqkv, const_cast<float*>(lse), dsum, rel_pos_h, rel_pos_w, batch, grid_side,
-                                     window, heads, head_dim, static_cast<cudaStream_t>(stream), true);
+                                     window, heads, head_dim, static_cast<cudaStream_t>(stream), true, tw_tab, th_tab);
 }
 
 int cvlm_op_ln_bwd(int xhat_kind, const float* gin, const float* gamma, const void* xsrc, const float* stat,

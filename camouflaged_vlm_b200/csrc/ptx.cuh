@@ -388,6 +388,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool 
     const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

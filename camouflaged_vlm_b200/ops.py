@@ -104,17 +104,21 @@ def attention(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tenso
 
 @_on_tensor_device
 def attention_lse(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, batch: int, grid: int,
-                  window: int, heads: int, head_dim: int):
+                  window: int, heads: int, head_dim: int, tables: bool = False):
     """``attention`` that also returns every token's row log-sum-exp (fp32 [rows, heads], log2 domain): what the training
     forward keeps for the backward kernels.  Only for the shapes of the tcgen05 kernels (64 x 64 global, 14 x 14 windows)."""
     _need_cuda(qkv, rel_pos_h, rel_pos_w)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
     out = torch.empty(qkv.shape[0], heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(qkv.shape[0], heads, device=qkv.device, dtype=torch.float32)
+    tw = th = None
+    if tables:      # 64 x 64 global blocks: every query's rel-pos terms for the dK / dV kernel, [rows, heads, 64] each
+        tw = torch.empty(qkv.shape[0], heads, 64, device=qkv.device, dtype=torch.float32)
+        th = torch.empty_like(tw)
     _lib.check(_lib.load().cvlm_op_attention_lse(qkv.data_ptr(), out.data_ptr(), rel_pos_h.contiguous().data_ptr(),
                                                  rel_pos_w.contiguous().data_ptr(), batch, grid, window, heads, head_dim,
-                                                 lse.data_ptr(), _lib.stream_ptr()), "cvlm_op_attention_lse")
-    return out, lse
+                                                 lse.data_ptr(), _ptr(tw), _ptr(th), _lib.stream_ptr()), "cvlm_op_attention_lse")
+    return (out, lse, tw, th) if tables else (out, lse)
 
 
 @_on_tensor_device
@@ -217,7 +221,7 @@ def adapter_embed(x0, hand, w_t, cst, batch, tokens, dim, rank, rank_pad) -> tor
 @_on_tensor_device
 def attention_backward(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, rel_pos_h: torch.Tensor,
                        rel_pos_w: torch.Tensor, batch: int, grid: int, window: int, heads: int, head_dim: int,
-                       lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       lse: Optional[torch.Tensor] = None, tables=None) -> torch.Tensor:
     """d(loss)/d(qkv) (bf16 [batch*grid^2, 3*D]) of ``attention`` given ``o`` (its output) and ``dout``.  ``lse`` (from
     ``attention_lse``) lets the kernels skip their own log-sum-exp sweep."""
     for t in (qkv, o, dout, rel_pos_h, rel_pos_w):
@@ -230,6 +234,8 @@ def attention_backward(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, r
         _lib.check(_lib.load().cvlm_op_attention_backward_lse(qkv.data_ptr(), o.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
                                                               lse.data_ptr(), dsum.data_ptr(), rel_pos_h.data_ptr(),
                                                               rel_pos_w.data_ptr(), batch, grid, window, heads, head_dim,
+                                                              _ptr(tables[0]) if tables else None,
+                                                              _ptr(tables[1]) if tables else None,
                                                               _lib.stream_ptr()), "cvlm_op_attention_backward_lse")
         return dqkv
     lse = torch.empty_like(dsum)

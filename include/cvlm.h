@@ -173,14 +173,19 @@ int cvlm_op_attention_backward(const void* qkv, const void* o, const void* dout,
                                int heads, int head_dim, cvlm_stream_t stream);
 /* cvlm_op_attention that also leaves every token's row log-sum-exp (log2 domain, relative-position terms included) in
  * lse, fp32 [batch*G*G, heads] -- what the training forward keeps for the backward kernels.  CVLM_ERR_UNSUPPORTED for
- * shapes that run on the mma.sync fallback kernel, which does not produce it. */
+ * shapes that run on the mma.sync fallback kernel, which does not produce it.  tw_tab / th_tab (both or neither; 64 x 64
+ * global blocks only): fp32 [batch*G*G, heads, 64] each, every query's relative-position terms laid out for the dK / dV
+ * kernel: tw[q][kx] = (q . rel_pos_w[qx - kx + 63]) log2(e), th[q][ky] likewise with rel_pos_h. */
 int cvlm_op_attention_lse(const void* qkv, void* out, const void* rel_pos_h, const void* rel_pos_w, int batch,
-                          int grid_side, int window, int heads, int head_dim, float* lse, cvlm_stream_t stream);
+                          int grid_side, int window, int heads, int head_dim, float* lse, float* tw_tab, float* th_tab,
+                          cvlm_stream_t stream);
 /* cvlm_op_attention_backward with lse already filled by cvlm_op_attention_lse: the kernels skip their own sweep over
- * S = q k^T that would compute it. */
+ * S = q k^T that would compute it; with the tables as well (may be NULL) the dK / dV kernel of the global blocks does not
+ * project the queries on the relative-position tables either and double-buffers its query tiles. */
 int cvlm_op_attention_backward_lse(const void* qkv, const void* o, const void* dout, void* dqkv, const float* lse,
                                    float* dsum, const void* rel_pos_h, const void* rel_pos_w, int batch, int grid_side,
-                                   int window, int heads, int head_dim, cvlm_stream_t stream);
+                                   int window, int heads, int head_dim, const float* tw_tab, const float* th_tab,
+                                   cvlm_stream_t stream);
 /* LayerNorm backward, one warp per row: dx = (residual ? residual : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),
  * g = gin * gamma (gamma NULL: already folded).  xhat_kind 0: xsrc = raw bf16 x, stat = (rstd, -mean*rstd) rows;
  * 1: xsrc = bf16 xhat, stat = rstd rows; 2: xsrc = fp32 x, statistics recomputed with eps.  dxb (optional) = bf16(dx). */

@@ -110,6 +110,22 @@ def test_attention_backward_with_the_forward_log_sum_exp(batch, grid, window, he
     got = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse)
     torch.cuda.synchronize()
     assert _rel(got, dqkv0) < 2e-3
+    if window == 0:
+        # global blocks: with the forward's per-query rel-pos terms the dK / dV kernel projects nothing itself
+        o2, lse2, tw, th = ops.attention_lse(qkv, relh, relw, batch, grid, window, heads, hd, tables=True)
+        assert torch.equal(o2, o) and torch.equal(lse2, lse)
+        q = qkv[:, :D].float().reshape(batch, grid, grid, heads, hd)
+        log2e = 1.4426950408889634
+        idx = (torch.arange(grid, device="cuda")[:, None] - torch.arange(grid, device="cuda")[None, :] + grid - 1)
+        want_tw = torch.einsum("byxhd,xkd->byxhk", q, relw.float()[idx]) * log2e          # [b, y, x, h, kx]
+        want_th = torch.einsum("byxhd,ykd->byxhk", q, relh.float()[idx]) * log2e          # [b, y, x, h, ky]
+        assert _rel(tw.reshape(batch, grid, grid, heads, 64), want_tw) < 1e-5
+        assert _rel(th.reshape(batch, grid, grid, heads, 64), want_th) < 1e-5
+        got_t = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse, tables=(tw, th))
+        torch.cuda.synchronize()
+        assert torch.equal(got_t[:, :D], got[:, :D])                 # dQ: same kernel
+        assert _rel(got_t, dqkv0) < 2e-3
+        got = got_t
     leaf = qkv.float().requires_grad_(True)
     (attention_reference(leaf, relh, relw, batch, grid, window, heads, hd) * dout.float()).sum().backward()
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
