@@ -106,21 +106,25 @@ __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
     return f32x2_fma(ax2, p, f32x2_relu(x2));
 }
 
-// d/dx of the exact-erf GELU, same erf approximation as gelu_erf:  gelu'(x) = Phi(x) + x * phi(x)
-// (backward of MLPBlock / lightweight_mlp for adapter training)
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-    const float ax = fabsf(x);
-    const float zs = ax * 0.8493218002880191f;                 // |x| / sqrt(2) * sqrt(log2 e)
-    float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2727374808792225f, zs, 1.0f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-zs * zs));             // exp(-x^2 / 2)
-    float p = fmaf(t, 0.5307027145f, -0.7265760135f);
-    p = fmaf(p, t, 0.7107068705f);
-    p = fmaf(p, t, -0.142248368f);
-    p = fmaf(p, t, 0.127414796f);
-    const float half_erfc = p * t * e;                          // 0.5 * erfc(|x| / sqrt 2)
-    const float phi_cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-    return fmaf(x * 0.3989422804014327f, e, phi_cdf);
+// gelu_erf2 that also returns gelu'(x) = Phi(x) + x phi(x) from the same intermediates (the training forward stores it
+// as bf16 for the backward pass: six more instructions here instead of a second erf + exp there).
+__device__ __forceinline__ uint64_t gelu_erf2_grad(uint64_t x2, uint64_t& g2) {
+    const uint64_t ax2 = f32x2_abs(x2);
+    const uint64_t zs2 = f32x2_mul(ax2, f32x2_pack(0.8493218002880191f, 0.8493218002880191f));
+    const uint64_t t2 = f32x2_rcp(f32x2_fma(zs2, f32x2_pack(0.2727374808792225f, 0.2727374808792225f), f32x2_pack(1.0f, 1.0f)));
+    const uint64_t e2 = f32x2_ex2_neg(f32x2_mul(zs2, zs2));                 // exp(-x^2 / 2)
+    uint64_t p = f32x2_fma(t2, f32x2_pack(-0.5307027145f, -0.5307027145f), f32x2_pack(0.7265760135f, 0.7265760135f));
+    p = f32x2_fma(p, t2, f32x2_pack(-0.7107068705f, -0.7107068705f));
+    p = f32x2_fma(p, t2, f32x2_pack(0.142248368f, 0.142248368f));
+    p = f32x2_fma(p, t2, f32x2_pack(-0.127414796f, -0.127414796f));
+    p = f32x2_mul(f32x2_mul(p, t2), e2);                                    // -0.5 erfc(|x| / sqrt 2)
+    float x0, x1, h0, h1, e0, e1;
+    f32x2_unpack(x2, x0, x1);
+    f32x2_unpack(p, h0, h1);
+    f32x2_unpack(e2, e0, e1);
+    const float c0 = x0 >= 0.f ? 1.0f + h0 : -h0, c1 = x1 >= 0.f ? 1.0f + h1 : -h1;      // Phi(x)
+    g2 = f32x2_pack(fmaf(x0 * 0.3989422804014327f, e0, c0), fmaf(x1 * 0.3989422804014327f, e1, c1));
+    return f32x2_fma(ax2, p, f32x2_relu(x2));
 }
 
 // PAIR = false: one CTA per 128 x 256 tile (small problems).
@@ -138,8 +142,9 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 //   F_STATIC    the epilogue type is a compile-time fact: F_BF16 (bf16 output), F_GELU, F_RES (fp32 residual) say which;
 //               without it those three are read from GemmEpi at run time (stem / adapter / neck GEMMs)
 constexpr int F_PRODUCER = 1, F_CONSUMER = 2, F_RARE = 4, F_STATIC = 8, F_BF16 = 16, F_GELU = 32, F_RES = 64, F_QUICK = 128;
-//   F_DGELU     bf16 path: multiply by gelu'(aux) (backward of a GELU layer).  On the bf16 path F_PRODUCER means "also
-//               store the PRE-activation value as bf16 in copy_bf16" (what that backward needs from the forward).
+//   F_DGELU     bf16 path: multiply by aux = gelu'(pre-activation) (backward of a GELU layer).  On the bf16 path
+//               F_PRODUCER means "also store what that backward needs in copy_bf16": gelu'(pre) for an erf-GELU layer,
+//               the pre-activation value otherwise.
 constexpr int F_DGELU = 256;
 // QuickGELU of CLIP (alpha_clip_rw/model.py:171-173): x * sigmoid(1.702 x); GemmArgs::act_gelu == 2
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -475,8 +480,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) y[e] = f32x2_add(y[e], bb[e]);
                             }
-                            if ((FEAT & F_PRODUCER) && ep.copy_bf16 != nullptr) {
-                                // training forward: keep the pre-activation value for the backward pass
+                            const bool keep = (FEAT & F_PRODUCER) && ep.copy_bf16 != nullptr;
+                            // training forward: what the backward pass needs of this layer goes to copy_bf16 -- gelu'(pre)
+                            // for an erf-GELU layer (the frozen trunk needs no weight gradient, so the pre-activation
+                            // itself is never read again), the pre-activation value otherwise
+                            const bool keep_grad = keep && act_gelu && !act_quick;
+                            if (keep && !keep_grad) {
                                 uint4 pre;
                                 float lo, hi;
                                 f32x2_unpack(y[0], lo, hi); pre.x = pack_bf16(lo, hi);
@@ -485,7 +494,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 f32x2_unpack(y[3], lo, hi); pre.w = pack_bf16(lo, hi);
                                 *reinterpret_cast<uint4*>(ep.copy_bf16 + (brow + row) * ep.ldc + col) = pre;
                             }
-                            if (act_gelu) {
+                            if (keep_grad) {
+                                uint64_t gq[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) y[e] = gelu_erf2_grad(y[e], gq[e]);
+                                uint4 gr;
+                                float lo, hi;
+                                f32x2_unpack(gq[0], lo, hi); gr.x = pack_bf16(lo, hi);
+                                f32x2_unpack(gq[1], lo, hi); gr.y = pack_bf16(lo, hi);
+                                f32x2_unpack(gq[2], lo, hi); gr.z = pack_bf16(lo, hi);
+                                f32x2_unpack(gq[3], lo, hi); gr.w = pack_bf16(lo, hi);
+                                *reinterpret_cast<uint4*>(ep.copy_bf16 + (brow + row) * ep.ldc + col) = gr;
+                            } else if (act_gelu) {
                                 if (act_quick) {
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) y[e] = quick_gelu2(y[e]);
@@ -501,8 +521,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
                                 for (int e = 0; e < 4; ++e) {
                                     float lo, hi;
                                     f32x2_unpack(y[e], lo, hi);
-                                    lo *= gelu_erf_grad(__uint_as_float(aw[e] << 16));
-                                    hi *= gelu_erf_grad(__uint_as_float(aw[e] & 0xffff0000u));
+                                    lo *= __uint_as_float(aw[e] << 16);            // aux holds gelu'(pre), see keep_grad
+                                    hi *= __uint_as_float(aw[e] & 0xffff0000u);
                                     y[e] = f32x2_pack(lo, hi);
                                 }
                             }

@@ -276,7 +276,8 @@ def wgrad_tn(a: torch.Tensor, b: torch.Tensor, ones: bool = False) -> torch.Tens
 
 @_on_tensor_device
 def gemm_bf16_dgelu(a: torch.Tensor, b: torch.Tensor, aux: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
-    """(a @ b.T) * gelu'(aux), bf16 out (the backward of a Linear -> GELU pair into the GELU's input)."""
+    """(a @ b.T) * aux, bf16 out: the backward of a Linear -> GELU pair into the GELU's input, with ``aux`` = gelu'(h) as
+    the training forward keeps it (``gemm_bf16(..., out_dtype=bf16, gelu=True, copy_bf16=aux)``)."""
     assert a.dtype == b.dtype == aux.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1 and aux.stride(1) == 1
     m, k = a.shape
     n = n or (b.shape[0] + 7) // 8 * 8

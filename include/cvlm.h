@@ -197,7 +197,8 @@ int cvlm_op_wgrad_tn_jp(int j, int ones);
 int cvlm_op_wgrad_tn_splits(long long m);
 int cvlm_op_wgrad_tn(const void* a, long long lda, int i_cols, const void* b, long long ldb, int j_cols, int ones,
                      long long m, float* scratch, float* out, cvlm_stream_t stream);
-/* cvlm_op_gemm_bf16 with the backward-of-GELU epilogue: out (bf16) = (A * B^T) * gelu'(aux[row, col]), aux bf16 [m, ldaux]. */
+/* cvlm_op_gemm_bf16 with the backward-of-GELU epilogue: out (bf16) = (A * B^T) * aux[row, col], aux bf16 [m, ldaux] =
+ * gelu'(pre-activation) as the training forward stores it (copy_bf16 of a bf16 GEMM with act_gelu = 1). */
 int cvlm_op_gemm_bf16_dgelu(const void* a, long long lda, const void* b, long long ldb, int k, int m, int n, int b_rows,
                             const void* aux, long long ldaux, void* out, long long ldo, cvlm_stream_t stream);
 

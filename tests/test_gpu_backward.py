@@ -217,10 +217,25 @@ def test_gemm_dgelu_epilogue(m, n, k):
     aux_full = _randn(m, ldaux, seed=32, scale=1.5, dtype=torch.bfloat16)
     aux = aux_full[:, n:2 * n] if ldaux != n else aux_full
     got = ops.gemm_bf16_dgelu(a, b, aux, n=n)
-    h = aux.float().requires_grad_(True)
-    F.gelu(h).sum().backward()
-    want = (a.float() @ b.float().t()) * h.grad
+    want = (a.float() @ b.float().t()) * aux.float()
     assert _rel(got, want) < 4e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 5120, 1280), (4096, 40, 1280), (1000, 64, 64)])
+def test_gelu_layer_keeps_its_derivative_for_the_backward(m, n, k):
+    """Training forward of a Linear -> GELU layer: the bf16 GEMM's second output is gelu'(pre-activation) (what the
+    backward-of-GELU epilogue multiplies by), computed from the same erf / exp as the GELU itself."""
+    a = _randn(m, k, seed=33, dtype=torch.bfloat16)
+    b = _randn(n, k, seed=34, scale=0.05, dtype=torch.bfloat16)
+    bias = _randn(n, seed=35, scale=0.5)
+    keep = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm_bf16(a, b, bias=bias, out_dtype=torch.bfloat16, gelu=True, copy_bf16=keep)
+    h = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    act = F.gelu(h)
+    act.sum().backward()
+    assert _rel(out, act.detach()) < 4e-3
+    assert _rel(keep, h.grad) < 4e-3
+    assert torch.equal(out, ops.gemm_bf16(a, b, bias=bias, out_dtype=torch.bfloat16, gelu=True))   # same GELU bits either way
 
 
 # ---------------------------------------------------------------------------------------------- whole module
