@@ -214,7 +214,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             uint32_t kph = 0, vph = 0;
             auto produce_k = [&](int u) {
                 if ((G2_PROBE & 2) && u >= NREL + G2_KST) return;
-                mbar_wait(k_empty(kst), kph ^ 1u);
+                mbar_wait_relaxed(k_empty(kst), kph ^ 1u);
                 const bool skip_hi = (G2_PROBE & 4) && u >= NREL;     // probe: 64 box rows per unit instead of 128
                 mbar_arrive_expect_tx(k_full(kst), skip_hi ? G2_KTILE : KV_BYTES);
                 if (!PLAIN && u < 2) {
@@ -232,7 +232,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             };
             auto produce_v = [&](int j) {
                 if ((G2_PROBE & 2) && j >= G2_VST) return;
-                mbar_wait(v_empty(vst), vph ^ 1u);
+                mbar_wait_relaxed(v_empty(vst), vph ^ 1u);
                 mbar_arrive_expect_tx(v_full(vst), (G2_PROBE & 4) ? G2_KTILE : KV_BYTES);
                 const int tok = tok0 + j * G2_UNIT;
                 tma_load_3d(sV(vst), &tmKV, v_full(vst), 0, 2 * heads + head, tok);

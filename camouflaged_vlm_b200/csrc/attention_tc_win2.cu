@@ -228,15 +228,15 @@ attn_window_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfl
                 const uint32_t ph = static_cast<uint32_t>(n & 1);          // one slot each: the phase flips per item
                 const int x0 = w.wx * W2_WS, y0 = w.wy * W2_WS;
                 if ((W2_PROBE & 2) && n > 0) break;
-                mbar_wait(q_empty, ph ^ 1u);
+                mbar_wait_relaxed(q_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(q_full, LOAD_BYTES);
                 tma_load_5d(sQ, &tmQKV, q_full, 0, w.head, x0, y0, w.b);
                 if (LOAD_HI) tma_load_5d(sQ + W2_TILE, &tmQKV, q_full, 64, w.head, x0, y0, w.b);
-                mbar_wait(k_empty, ph ^ 1u);
+                mbar_wait_relaxed(k_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(k_full, LOAD_BYTES);
                 tma_load_5d(sK, &tmQKV, k_full, 0, heads + w.head, x0, y0, w.b);
                 if (LOAD_HI) tma_load_5d(sK + W2_KTILE, &tmQKV, k_full, 64, heads + w.head, x0, y0, w.b);
-                mbar_wait(v_empty, ph ^ 1u);
+                mbar_wait_relaxed(v_empty, ph ^ 1u);
                 mbar_arrive_expect_tx(v_full, LOAD_BYTES);
                 tma_load_5d(sV, &tmQKV, v_full, 0, 2 * heads + w.head, x0, y0, w.b);
                 if (LOAD_HI) tma_load_5d(sV + W2_TILE, &tmQKV, v_full, 64, 2 * heads + w.head, x0, y0, w.b);
