@@ -171,6 +171,28 @@ def test_forward_host_pipelines_chunks_and_matches_forward():
     assert got.is_pinned() and torch.equal(got, want.cpu())
 
 
+@pytest.mark.parametrize("python_path", [False, True])
+def test_forward_host_back_to_back_calls_overlap_safely(python_path):
+    """Consecutive forward_host calls are not separated by a stream edge any more: the first upload of a call runs under
+    the last encoder of the previous one, and a staging half only waits for the encoder that last read it.  Several
+    calls with different inputs, no synchronisation in between, odd and even chunk counts: every result must be the
+    bits of a plain device forward.  python_path=True goes through the on_chunk choreography (what N > 1 uses)."""
+    cfg = PRESETS["tiny"]
+    m = _encoder(cfg)
+    xs = [seeded_images(cfg, b, seed).pin_memory() for b, seed in ((5, 0), (4, 1), (1, 2), (6, 3), (3, 4))]
+    seen = []
+    hook = (lambda s, e, emb: seen.append((s, e))) if python_path else None
+    outs = []
+    with torch.no_grad():
+        for x in xs:                                     # no synchronisation between the calls
+            outs.append(m.forward_host(x, chunk=2, on_chunk=hook))
+        torch.cuda.synchronize()
+        for x, got in zip(xs, outs):
+            assert torch.equal(got, m(x.cuda()).cpu())
+    if python_path:
+        assert len(seen) == sum(-(-x.shape[0] // 2) for x in xs)
+
+
 def test_graphed_encoder_replays_bit_identically():
     """CUDA-graph replay (camouflaged_vlm_b200.graphed): same bits as the eager forward, new inputs each call."""
     from camouflaged_vlm_b200.graphed import GraphedEncoder
