@@ -45,8 +45,8 @@ struct BwdParams {
     float scale, scale_log2;
     int lse_ready;              // lse was written by the forward kernel: the specialised kernels skip their own S sweep for it
     // 64 x 64 global blocks, written by the training forward (attention_tc2.cu), log2 domain, fp32 [B*G*G, heads, 64] each:
-    // tw_tab[q][kx] = T_w[q][qx - kx + 63] and th_tab[q][ky] = T_h[q][qy - ky + 63]; NULL: the kernels project q on the
-    // rel-pos tables themselves
+    // tw_tab[q][kx] = T_w[q][qx - kx + 63] - lse[q] and th_tab[q][ky] = T_h[q][qy - ky + 63]; NULL: the kernels project q
+    // on the rel-pos tables themselves
     const float* tw_tab;
     const float* th_tab;
 };
@@ -1314,7 +1314,6 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64t_kernel(const Bw
         if (tid < BW_T) {
             float* sRow = stRow(st);
             const long long row = (tok_base + qt * 64 + tid) * p.heads + head;
-            cp_async_4(smem_u32(sRow + tid), p.lse + row);
             cp_async_4(smem_u32(sRow + BW_T + tid), p.dsum + row);
             cp_async_4(smem_u32(sRow + 2 * BW_T + tid), p.th_tab + row * 64 + kt);
         }
@@ -1358,8 +1357,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64t_kernel(const Bw
         const __nv_bfloat16* sQ = stQ(st);
         const __nv_bfloat16* sdO = sQ + BW_T * HDP;
         const float* sTw = stTw(st);
-        const float* sLse = stRow(st);
-        const float* sD = sLse + BW_T;
+        const float* sD = stRow(st) + BW_T;
         const float* sThc = sD + BW_T;
         float s[8][4], dp[8][4];
 #pragma unroll
@@ -1387,7 +1385,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv64t_kernel(const Bw
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int q = nt * 8 + 2 * t + e;             // query column = qx
-                const float c = sThc[q] - sLse[q], dd = sD[q];
+                const float c = sThc[q], dd = sD[q];          // (the row's log-sum-exp is already inside the T_w table)
                 const float* tw = sTw + q * TWS;              // bank = (4 q + kx) mod 32: distinct over the warp
                 const float l0 = fmaf(s[nt][e], p.scale_log2, c + tw[kx0]);
                 const float l1 = fmaf(s[nt][2 + e], p.scale_log2, c + tw[kx1]);
@@ -1854,6 +1852,10 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
         CVLM_TRY(ensure_dynamic_smem(attn_bwd_dq64_kernel<HD>, Bwd64Smem<HD>::dq_total, g0));
         attn_bwd_dq64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dq_total, stream>>>(p);
         CVLM_CUDA(cudaGetLastError());
+        if (p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready && option(OPT_BWD_TC) != 0) {
+            // tcgen05 kernel (attention_bwd_tc.cu); cvlm_set_option("bwd_tc", 0) keeps the mma.sync kernel below for A/B runs
+            return attention_bwd_dkv_tc_launch(p.qkv, p.dout, p.dqkv, p.dsum, p.tw_tab, p.th_tab, batch, p.heads, HD, stream);
+        }
         if (p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready) {
             static unsigned char g2[kMaxDevices] = {};
             CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64t_kernel<HD>, Bwd64Smem<HD>::dkvt_total, g2));

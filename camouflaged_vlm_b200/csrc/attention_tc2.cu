@@ -429,11 +429,13 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         __nv_bfloat16* orow = out + (static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * D + head * HD;
         const bool live = !PLAIN || qb * 256 + t * 128 + r < L;        // query rows beyond the sequence are not stored
         // training forward: the row's log-sum-exp (log2 domain, rel-pos terms included) for the backward kernels
+        const float lse_row = m_used + log2f(l);
         if (lse_out != nullptr && live)
-            lse_out[(static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head] = m_used + log2f(l);
+            lse_out[(static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head] = lse_row;
         if (!PLAIN && tw_out != nullptr && th_out != nullptr) {
-            // ... and this row's rel-pos terms as the dK / dV kernel wants them (it walks the queries as columns and cannot
-            // project them itself without a third of its MMAs): tw[kx] = T_w[q][qx - kx + 63], th[ky] = T_h[q][qy - ky + 63]
+            // ... and this row's rel-pos terms as the dK / dV kernels want them (they walk the queries as columns and cannot
+            // project them themselves without a third of their MMAs): tw[kx] = T_w[q][qx - kx + 63] - lse[q] (so that
+            // P = exp2(s * scale + tw + th) needs no further per-query term), th[ky] = T_h[q][qy - ky + 63]
             const long long row = (static_cast<long long>(tok0) + qb * 256 + t * 128 + r) * heads + head;
             float4* twp = reinterpret_cast<float4*>(tw_out + row * 64);
             float4* thp = reinterpret_cast<float4*>(th_out + row * 64);
@@ -442,7 +444,7 @@ attn_global_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 float a0, a1, a2, a3;
                 f32x2_unpack(tw2[2 * i], a0, a1);
                 f32x2_unpack(tw2[2 * i + 1], a2, a3);
-                twp[i] = make_float4(a0, a1, a2, a3);
+                twp[i] = make_float4(a0 - lse_row, a1 - lse_row, a2 - lse_row, a3 - lse_row);
             }
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {

@@ -44,7 +44,7 @@ int ensure_dynamic_smem(Kern kern, int bytes, unsigned char* flags) {
     return CVLM_OK;
 }
 // cvlm_set_option (include/cvlm.h): read on the launch path as one relaxed atomic load, never getenv
-enum Option { OPT_GEMM_MODE = 0, OPT_DEC_CLUSTER, OPT_ATTN_LEGACY, OPT_ATTN_POLY, OPT_WIN_MODE, OPT_COUNT };
+enum Option { OPT_GEMM_MODE = 0, OPT_DEC_CLUSTER, OPT_ATTN_LEGACY, OPT_ATTN_POLY, OPT_WIN_MODE, OPT_BWD_TC, OPT_COUNT };
 int option(Option o);
 
 // ---- GEMM (gemm_tcgen05.cu):  out = epilogue(A1 * B1^T [+ A2 * B2^T])
@@ -126,6 +126,9 @@ int attention_backward_launch(const void* qkv, const void* o, const void* dout, 
                               const void* relh, const void* relw, int batch, int grid_side, int window, int heads,
                               int head_dim, cudaStream_t stream, bool lse_ready = false, const float* tw_tab = nullptr,
                               const float* th_tab = nullptr);
+// dK / dV of a 64 x 64 global block on tcgen05 (attention_bwd_tc.cu); dsum must hold D = rowsum(dO o) (the dQ kernel writes it)
+int attention_bwd_dkv_tc_launch(const void* qkv, const void* dout, void* dqkv, const float* dsum, const float* tw_tab,
+                                const float* th_tab, int batch, int heads, int head_dim, cudaStream_t stream);
 int layernorm_train_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, void* xhat_bf16,
                            float* rstd, long long rows, int cols, float eps, cudaStream_t stream);
 int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void* xsrc, const float* stat,

@@ -80,6 +80,42 @@ inline int make_tensor_map_bf16(CUtensorMap* out, MapSpec spec) {
     return CVLM_OK;
 }
 
+// fp32 tensor, no swizzle (rows land in shared memory as they are in global memory), zero fill out of bounds.
+inline int make_tensor_map_f32_plain(CUtensorMap* out, MapSpec spec) {
+    static std::mutex mu;
+    static std::unordered_map<MapSpec, CUtensorMap, MapSpecHash> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(spec);
+        if (it != cache.end()) {
+            *out = it->second;
+            return CVLM_OK;
+        }
+    }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(CVLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (reinterpret_cast<uintptr_t>(spec.ptr) & 15) return set_error(CVLM_ERR_ARG, "tensor map: base not 16-byte aligned");
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    if (spec.rank < 1 || spec.rank > 5) return set_error(CVLM_ERR_ARG, "tensor map: rank %d", spec.rank);
+    for (int i = 0; i < spec.rank; ++i) {
+        dims[i] = spec.dims[i];
+        box[i] = spec.box[i];
+    }
+    for (int i = 0; i + 1 < spec.rank; ++i) {
+        if (spec.strides[i] & 15) return set_error(CVLM_ERR_ARG, "tensor map: stride not a multiple of 16 bytes");
+        strides[i] = spec.strides[i];
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, spec.rank, const_cast<void*>(spec.ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(CVLM_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache[spec] = *out;
+    return CVLM_OK;
+}
+
 inline MapSpec map_spec_zero() {
     MapSpec s;
     memset(&s, 0, sizeof(s));

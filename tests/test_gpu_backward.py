@@ -119,12 +119,19 @@ def test_attention_backward_with_the_forward_log_sum_exp(batch, grid, window, he
         idx = (torch.arange(grid, device="cuda")[:, None] - torch.arange(grid, device="cuda")[None, :] + grid - 1)
         want_tw = torch.einsum("byxhd,xkd->byxhk", q, relw.float()[idx]) * log2e          # [b, y, x, h, kx]
         want_th = torch.einsum("byxhd,ykd->byxhk", q, relh.float()[idx]) * log2e          # [b, y, x, h, ky]
-        assert _rel(tw.reshape(batch, grid, grid, heads, 64), want_tw) < 1e-5
+        # (the T_w table carries the row's log-sum-exp: tw = T_w - lse, so that P = exp2(s * scale + tw + th))
+        assert _rel(tw.reshape(batch, grid, grid, heads, 64) + lse.reshape(batch, grid, grid, heads, 1), want_tw) < 1e-5
         assert _rel(th.reshape(batch, grid, grid, heads, 64), want_th) < 1e-5
-        got_t = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse, tables=(tw, th))
-        torch.cuda.synchronize()
-        assert torch.equal(got_t[:, :D], got[:, :D])                 # dQ: same kernel
-        assert _rel(got_t, dqkv0) < 2e-3
+        for tc in (0, 1):       # mma.sync kernel with the tables (double-buffered) / tcgen05 kernel (attention_bwd_tc.cu)
+            _lib.set_option("bwd_tc", tc)
+            try:
+                got_t = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse, tables=(tw, th))
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option("bwd_tc", 1)
+            assert torch.equal(got_t[:, :D], got[:, :D])             # dQ: same kernel
+            assert _rel(got_t[:, D:2 * D], dqkv0[:, D:2 * D]) < 3e-3, f"dK, bwd_tc={tc}"
+            assert _rel(got_t[:, 2 * D:], dqkv0[:, 2 * D:]) < 3e-3, f"dV, bwd_tc={tc}"
         got = got_t
     leaf = qkv.float().requires_grad_(True)
     (attention_reference(leaf, relh, relw, batch, grid, window, heads, hd) * dout.float()).sum().backward()
