@@ -1849,13 +1849,20 @@ int launch_bwd(const BwdParams& p, int batch, cudaStream_t stream) {
     if (p.S == 64 && p.G == 64 && HD >= 64 && option(OPT_ATTN_LEGACY) == 0) {   // the 64 x 64 global blocks: specialised kernels
         static unsigned char g0[kMaxDevices] = {}, g1[kMaxDevices] = {};
         dim3 grid64(64, p.heads, batch);
-        CVLM_TRY(ensure_dynamic_smem(attn_bwd_dq64_kernel<HD>, Bwd64Smem<HD>::dq_total, g0));
-        attn_bwd_dq64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dq_total, stream>>>(p);
-        CVLM_CUDA(cudaGetLastError());
-        if (p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready && option(OPT_BWD_TC) != 0) {
-            // tcgen05 kernel (attention_bwd_tc.cu); cvlm_set_option("bwd_tc", 0) keeps the mma.sync kernel below for A/B runs
-            return attention_bwd_dkv_tc_launch(p.qkv, p.dout, p.dqkv, p.dsum, p.tw_tab, p.th_tab, batch, p.heads, HD, stream);
+        const bool tabs = p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready;
+        // tcgen05 kernels (attention_bwd_tc.cu) when the training forward left its tables; cvlm_set_option("bwd_tc", v):
+        // 0 = mma.sync kernels only, 1 = dK / dV on tcgen05, 2 (default) = dQ as well
+        const int tc = tabs ? option(OPT_BWD_TC) : 0;
+        if (tc >= 2) {
+            CVLM_TRY(attention_bwd_dq_tc_launch(p.qkv, p.o, p.dout, p.dqkv, p.dsum, p.tw_tab, p.th_tab, p.relh, p.relw, batch,
+                                                p.heads, HD, stream));
+        } else {
+            CVLM_TRY(ensure_dynamic_smem(attn_bwd_dq64_kernel<HD>, Bwd64Smem<HD>::dq_total, g0));
+            attn_bwd_dq64_kernel<HD><<<grid64, BW_THREADS, Bwd64Smem<HD>::dq_total, stream>>>(p);
+            CVLM_CUDA(cudaGetLastError());
         }
+        if (tc >= 1)
+            return attention_bwd_dkv_tc_launch(p.qkv, p.dout, p.dqkv, p.dsum, p.tw_tab, p.th_tab, batch, p.heads, HD, stream);
         if (p.tw_tab != nullptr && p.th_tab != nullptr && p.lse_ready) {
             static unsigned char g2[kMaxDevices] = {};
             CVLM_TRY(ensure_dynamic_smem(attn_bwd_dkv64t_kernel<HD>, Bwd64Smem<HD>::dkvt_total, g2));

@@ -298,6 +298,392 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// dQ of the same blocks (and D = rowsum(dO o), which the dK / dV kernel reads).  One CTA owns 128 QUERIES (two grid rows) and
+// streams the 64 key units (one grid row each); thread = query row, and -- because every per-row term (lse, D, the rel-pos
+// terms) is known before the first unit -- the two softmax warpgroups again split the unit's 64 key columns without talking
+// to each other:
+//   S(u) = Q K_u^T,  dP(u) = dO V_u^T          SS, M128 N64 -> TMEM (two buffers each)
+//   dS = exp2(S * scale + tw[kx] + th[ky = u]) * (dP - D)      dSh[q][u] += sum_kx dS (a scalar per unit and thread),
+//                                                              dSw[q][kx] += dS (32 registers per thread)
+//   dQ += (scale * dS) K_u                      TS, K_u MN-major from the tile the SS MMA read K-major
+// and at the end  dQ += dT_h R_h + dT_w R_w  with  dT_h[q][j] = dSh[q][qy + 63 - j],  dT_w[q][j] = dSw[q][qx + 63 - j]:
+// each warpgroup writes its PARTIAL dT rows (bf16) over the retired S / dP buffers and the MMA adds all four products; the
+// two tables travel through the unit ring as "units" 64 and 65.
+constexpr int BQ_STAGE = 4 * BT_UT;                 // K lo|hi, V lo|hi (or one rel-pos table: rows 0..63 | 64..127)
+constexpr int BQ_OFF_Q = 0, BQ_OFF_DO = 2 * BT_KT, BQ_OFF_ST = 4 * BT_KT;
+constexpr int BQ_OFF_BAR = BQ_OFF_ST + BT_NST * BQ_STAGE;
+constexpr int BQ_SMEM = BQ_OFF_BAR + 256 + 1024;
+constexpr uint32_t BQ_COL_DQ = 256;
+
+struct BqParams {
+    const float* tw_tab;          // [B*4096, heads, 64]  T_w[q][qx - kx + 63] - lse[q]
+    const float* th_tab;          // [B*4096, heads, 64]  T_h[q][qy - ky + 63]
+    const __nv_bfloat16* o;       // [B*4096, D] forward output
+    const __nv_bfloat16* dout;    // [B*4096, D]
+    float* dsum;                  // [B*4096, heads] out: D
+    __nv_bfloat16* dqkv;          // [B*4096, 3*D]
+    int heads, D;
+    float scale, scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
+                      const __grid_constant__ CUtensorMap tmKV64, const __grid_constant__ CUtensorMap tmRelH,
+                      const __grid_constant__ CUtensorMap tmRelW, const BqParams p) {
+    constexpr bool HI = HD > 64;
+    constexpr uint32_t T_BYTES = (HI ? 2 : 1) * BT_KT;
+    constexpr uint32_t U_BYTES = (HI ? 2 : 1) * BT_UT;
+    constexpr int NK = 4096 / BT_UNIT;               // key units; units NK, NK + 1 of the ring are the two tables
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQ = base + BQ_OFF_Q, sDO = base + BQ_OFF_DO;
+    auto sK = [&](int st) { return base + BQ_OFF_ST + st * BQ_STAGE; };
+    auto sV = [&](int st) { return sK(st) + 2 * BT_UT; };
+    const uint32_t bars = base + BQ_OFF_BAR;
+    const uint32_t qd_full = bars;
+    auto st_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto st_empty = [&](int s) { return bars + 8u * (4 + s); };
+    auto sdp_full = [&](int b) { return bars + 8u * (7 + b); };
+    auto ds_full = [&](int b) { return bars + 8u * (9 + b); };
+    const uint32_t dq_done = bars + 8u * 11, dt_full = bars + 8u * 12, acc_full = bars + 8u * 13;
+    const uint32_t tmem_slot = bars + 8u * 14;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(base_ptr + BQ_OFF_BAR + 8 * 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int heads = p.heads;
+    const int tok0 = b * 4096;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ128);
+        tma_prefetch_desc(&tmDO128);
+        tma_prefetch_desc(&tmKV64);
+        tma_prefetch_desc(&tmRelH);
+        tma_prefetch_desc(&tmRelW);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(qd_full, 1);
+        for (int s = 0; s < BT_NST; ++s) {
+            mbar_init(st_full(s), 1);
+            mbar_init(st_empty(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(sdp_full(i), 1);
+            mbar_init(ds_full(i), 256);
+        }
+        mbar_init(dq_done, 1);
+        mbar_init(dt_full, 256);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < 4) {
+        setmaxnreg_dec<64>();
+        if (warp == 0 && elect_one_sync()) {
+            // ============================================================ TMA producer
+            mbar_arrive_expect_tx(qd_full, 2 * T_BYTES);
+            const int qtok = tok0 + qt * 128;
+            tma_load_3d(sQ, &tmQ128, qd_full, 0, head, qtok);
+            if (HI) tma_load_3d(sQ + BT_KT, &tmQ128, qd_full, 64, head, qtok);
+            tma_load_3d(sDO, &tmDO128, qd_full, 0, head, qtok);
+            if (HI) tma_load_3d(sDO + BT_KT, &tmDO128, qd_full, 64, head, qtok);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int u = 0; u < NK + 2; ++u) {
+                mbar_wait_relaxed(st_empty(st), ph ^ 1u);
+                mbar_arrive_expect_tx(st_full(st), 2 * U_BYTES);
+                if (u < NK) {
+                    const int ktok = tok0 + u * BT_UNIT;
+                    tma_load_3d(sK(st), &tmKV64, st_full(st), 0, heads + head, ktok);
+                    if (HI) tma_load_3d(sK(st) + BT_UT, &tmKV64, st_full(st), 64, heads + head, ktok);
+                    tma_load_3d(sV(st), &tmKV64, st_full(st), 0, 2 * heads + head, ktok);
+                    if (HI) tma_load_3d(sV(st) + BT_UT, &tmKV64, st_full(st), 64, 2 * heads + head, ktok);
+                } else {
+                    const CUtensorMap* tm = u == NK ? &tmRelH : &tmRelW;     // rows 0..63 | 64..127 (row 127: zeros)
+                    tma_load_2d(sK(st), tm, st_full(st), 0, 0);
+                    if (HI) tma_load_2d(sK(st) + BT_UT, tm, st_full(st), 64, 0);
+                    tma_load_2d(sV(st), tm, st_full(st), 0, 64);
+                    if (HI) tma_load_2d(sV(st) + BT_UT, tm, st_full(st), 64, 64);
+                }
+                if (++st == BT_NST) { st = 0; ph ^= 1u; }
+            }
+        } else if (warp == 1 && elect_one_sync()) {
+            // ============================================================ MMA issuer
+            constexpr uint32_t idescS = umma_idesc_bf16(128, BT_UNIT);
+            constexpr uint32_t idescO = umma_idesc_bf16_bmn(128, HD);
+            mbar_wait(qd_full, 0);
+            tc_fence_after();
+            const uint64_t q_lo = umma_desc_k_sw128(sQ), q_hi = umma_desc_k_sw128(sQ + BT_KT);
+            const uint64_t d_lo = umma_desc_k_sw128(sDO), d_hi = umma_desc_k_sw128(sDO + BT_KT);
+            const uint32_t tDQ = tmem_base + BQ_COL_DQ;
+            auto issue_dq = [&](int j) {             // dQ += (scale dS(j)) K_j
+                const int stj = j % BT_NST, bj = j & 1;
+                mbar_wait(ds_full(bj), static_cast<uint32_t>((j >> 1) & 1));
+                tc_fence_after();
+                const uint64_t k_mn = umma_desc_mn_sw128(sK(stj), BT_UT);
+                const uint32_t aDS = tmem_base + BT_COL_S + bj * 64;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t pc = (kk & 1) * 8u + (kk >> 1) * 32u;
+                    umma_bf16_ts(tDQ, aDS + pc, k_mn + 128u * kk, idescO, (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(st_empty(stj));
+            };
+            int st = 0;
+            uint32_t ph = 0;
+            for (int u = 0; u < NK; ++u) {
+                mbar_wait(st_full(st), ph);
+                tc_fence_after();
+                const int bu = u & 1;
+                const uint64_t k_lo = umma_desc_k_sw128(sK(st)), k_hi = umma_desc_k_sw128(sK(st) + BT_UT);
+                const uint64_t v_lo = umma_desc_k_sw128(sV(st)), v_hi = umma_desc_k_sw128(sV(st) + BT_UT);
+                const uint32_t tS = tmem_base + BT_COL_S + bu * 64, tDP = tmem_base + BT_COL_DP + bu * 64;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, q_lo + 2u * k, k_lo + 2u * k, idescS, k > 0);
+                if (HI) umma_bf16_ss(tS, q_hi, k_hi, idescS, 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ss(tDP, d_lo + 2u * k, v_lo + 2u * k, idescS, k > 0);
+                if (HI) umma_bf16_ss(tDP, d_hi, v_hi, idescS, 1);
+                umma_commit(sdp_full(bu));
+                if (u >= 1) issue_dq(u - 1);
+                if (++st == BT_NST) { st = 0; ph ^= 1u; }
+            }
+            issue_dq(NK - 1);
+            umma_commit(dq_done);                    // S / dP buffers are free once this fires: the dT rows go there
+            // ---- dQ += dT_h R_h + dT_w R_w: four partial dT operands (two warpgroups x {h, w}), 128 table rows each
+            int st_tab[2];
+            for (int i = 0; i < 2; ++i) {
+                mbar_wait(st_full(st), ph);
+                st_tab[i] = st;
+                if (++st == BT_NST) { st = 0; ph ^= 1u; }
+            }
+            mbar_wait(dt_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {            // i = 0: rel_pos_h, 1: rel_pos_w
+                const uint64_t r0 = umma_desc_mn_sw128(sK(st_tab[i]), BT_UT), r1 = umma_desc_mn_sw128(sV(st_tab[i]), BT_UT);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const uint32_t aT = tmem_base + (i == 0 ? BT_COL_S : BT_COL_DP) + w * 64;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16_ts(tDQ, aT + 8u * kk, (kk < 4 ? r0 + 128u * kk : r1 + 128u * (kk - 4)), idescO, 1u);
+                }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ============================================================ dS: thread = query row, 32 key columns
+        setmaxnreg_inc<216>();
+        const int w = warp >= 8 ? 1 : 0;
+        const int r = threadIdx.x - 128 - w * 128;          // query row 0..127 of the tile
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int qy_rel = r >> 6, qx = r & 63;              // qy = 2 qt + qy_rel
+        const long long tok = static_cast<long long>(tok0) + qt * 128 + r;
+        const long long row = tok * heads + head;
+        // ---- per-row terms: D = rowsum(dO o); tw for this warpgroup's 32 kx; the whole th row (indexed by the unit)
+        float dsum = 0.f;
+        {
+            const __nv_bfloat16* po = p.o + tok * p.D + head * HD;
+            const __nv_bfloat16* pd = p.dout + tok * p.D + head * HD;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                const uint4 a = *reinterpret_cast<const uint4*>(po + c * 8), g = *reinterpret_cast<const uint4*>(pd + c * 8);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    dsum = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), dsum);
+                    dsum = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), dsum);
+                }
+            }
+            if (w == 0) p.dsum[row] = dsum;
+        }
+        float tw[32], th_l[64], dsw[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(p.tw_tab + row * 64 + 32 * w + 4 * i);
+            tw[4 * i] = v.x; tw[4 * i + 1] = v.y; tw[4 * i + 2] = v.z; tw[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(p.th_tab + row * 64 + 4 * i);
+            th_l[4 * i] = v.x; th_l[4 * i + 1] = v.y; th_l[4 * i + 2] = v.z; th_l[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dsw[i] = 0.f;
+        const uint32_t col = 32u * w;
+#pragma unroll 1
+        for (int u = 0; u < NK; ++u) {
+            const int bu = u & 1;
+            const float th = th_l[u];
+            mbar_wait(sdp_full(bu), static_cast<uint32_t>((u >> 1) & 1));
+            tc_fence_after();
+            const uint32_t tS = tmem_base + lane_addr + BT_COL_S + bu * 64, tDP = tmem_base + lane_addr + BT_COL_DP + bu * 64;
+            uint32_t vs[32], vd[32];
+            tmem_ld_32x32(tS + col, vs);
+            tmem_ld_32x32(tDP + col, vd);
+            tmem_ld_wait(vs);
+            tmem_ld_wait(vd);
+            uint32_t pk[16];
+            float rs = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                float ds[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float x = fmaf(__uint_as_float(vs[c + e]), p.scale_log2, tw[c + e] + th);
+                    ds[e] = bt_ex2(x) * (__uint_as_float(vd[c + e]) - dsum);
+                    dsw[c + e] += ds[e];
+                    rs += ds[e];
+                }
+                pk[c >> 1] = pack_bf16(ds[0] * p.scale, ds[1] * p.scale);
+            }
+            th_l[u] = rs;                                // dSh[q][ky = u] (this warpgroup's share) takes the consumed slot
+            tmem_st_32x16(tS + col, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(ds_full(bu));
+        }
+        // ---- partial dT rows over the retired buffers: dT_h at S[w], dT_w at dP[w]; column c holds table rows 2c, 2c + 1
+        float dsw_l[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dsw_l[i] = dsw[i];
+        mbar_wait(dq_done, 0);
+        tc_fence_after();
+        const int qy = 2 * qt + qy_rel;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t hk[32], wk[32];
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+                float hv[2], wv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = half * 64 + 2 * c + e;                 // table row
+                    const int ky = qy + 63 - j, kxw = qx + 63 - j - 32 * w;
+                    hv[e] = (ky >= 0 && ky < 64) ? th_l[ky] : 0.f;
+                    wv[e] = (kxw >= 0 && kxw < 32) ? dsw_l[kxw] : 0.f;
+                }
+                hk[c] = pack_bf16(hv[0], hv[1]);
+                wk[c] = pack_bf16(wv[0], wv[1]);
+            }
+            tmem_st_32x32(tmem_base + lane_addr + BT_COL_S + w * 64 + half * 32, hk);
+            tmem_st_32x32(tmem_base + lane_addr + BT_COL_DP + w * 64 + half * 32, wk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(dt_full);
+        // ---- epilogue: dQ -> bf16 -> global; warpgroup 0 stores d 0..31 (and 64..79), warpgroup 1 d 32..63
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.dqkv + tok * (3LL * p.D) + head * HD;
+        uint32_t va[32];
+        tmem_ld_32x32(tmem_base + lane_addr + BQ_COL_DQ + 32 * w, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+            o4.y = pack_bf16(__uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+            o4.z = pack_bf16(__uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+            o4.w = pack_bf16(__uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+            *reinterpret_cast<uint4*>(orow + 32 * w + i) = o4;
+        }
+        if (HI && w == 0) {
+            uint32_t w16[16];
+            tmem_ld_32x16(tmem_base + lane_addr + BQ_COL_DQ + 64, w16);
+            tmem_ld_wait16(w16);
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+                uint4 o4;
+                o4.x = pack_bf16(__uint_as_float(w16[i]), __uint_as_float(w16[i + 1]));
+                o4.y = pack_bf16(__uint_as_float(w16[i + 2]), __uint_as_float(w16[i + 3]));
+                o4.z = pack_bf16(__uint_as_float(w16[i + 4]), __uint_as_float(w16[i + 5]));
+                o4.w = pack_bf16(__uint_as_float(w16[i + 6]), __uint_as_float(w16[i + 7]));
+                *reinterpret_cast<uint4*>(orow + 64 + i) = o4;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int HD>
+int launch_dq_tc(const void* qkv, const void* o, const void* dout, void* dqkv, float* dsum, const float* tw_tab,
+                 const float* th_tab, const void* relh, const void* relw, int batch, int heads, cudaStream_t stream) {
+    const int D = heads * HD;
+    const unsigned long long M = 4096ull * batch;
+    CUtensorMap tq, tdo, tkv, trh, trw;
+    MapSpec s = map_spec_zero();
+    s.ptr = qkv;
+    s.rank = 3;
+    s.dims[0] = HD; s.dims[1] = 3ull * heads; s.dims[2] = M;
+    s.strides[0] = HD * 2ull; s.strides[1] = 3ull * D * 2;
+    s.box[0] = 64; s.box[1] = 1; s.box[2] = 128;
+    CVLM_TRY(make_tensor_map_bf16(&tq, s));
+    s.box[2] = BT_UNIT;
+    CVLM_TRY(make_tensor_map_bf16(&tkv, s));
+    MapSpec d = map_spec_zero();
+    d.ptr = dout;
+    d.rank = 3;
+    d.dims[0] = HD; d.dims[1] = heads; d.dims[2] = M;
+    d.strides[0] = HD * 2ull; d.strides[1] = D * 2ull;
+    d.box[0] = 64; d.box[1] = 1; d.box[2] = 128;
+    CVLM_TRY(make_tensor_map_bf16(&tdo, d));
+    MapSpec r = map_spec_zero();
+    r.rank = 2;
+    r.dims[0] = HD; r.dims[1] = 127;
+    r.strides[0] = HD * 2ull;
+    r.box[0] = 64; r.box[1] = 64;
+    r.ptr = relh;
+    CVLM_TRY(make_tensor_map_bf16(&trh, r));
+    r.ptr = relw;
+    CVLM_TRY(make_tensor_map_bf16(&trw, r));
+    auto kern = attn_bwd_dq_tc_kernel<HD>;
+    static unsigned char ready[kMaxDevices] = {};
+    {
+        int dev = 0;
+        CVLM_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= kMaxDevices || !__atomic_load_n(&ready[dev], __ATOMIC_ACQUIRE)) {
+            cudaFuncAttributes fa;
+            CVLM_CUDA(cudaFuncGetAttributes(&fa, kern));
+            if ((fa.numRegs - 64) * 128 < (216 - fa.numRegs) * 256)
+                return set_error(CVLM_ERR_UNSUPPORTED, "attention_bwd_tc: built with %d registers per thread; the setmaxnreg pool would be short", fa.numRegs);
+        }
+    }
+    CVLM_TRY(ensure_dynamic_smem(kern, BQ_SMEM, ready));
+    BqParams p;
+    p.tw_tab = tw_tab;
+    p.th_tab = th_tab;
+    p.o = static_cast<const __nv_bfloat16*>(o);
+    p.dout = static_cast<const __nv_bfloat16*>(dout);
+    p.dsum = dsum;
+    p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    p.heads = heads;
+    p.D = D;
+    p.scale = 1.0f / sqrtf(static_cast<float>(HD));
+    p.scale_log2 = p.scale * kLog2eBT;
+    dim3 grid(4096 / 128, heads, batch);
+    kern<<<grid, BT_THREADS, BQ_SMEM, stream>>>(tq, tdo, tkv, trh, trw, p);
+    CVLM_CUDA(cudaGetLastError());
+    return CVLM_OK;
+}
+
 template <int HD>
 int launch_dkv_tc(const void* qkv, const void* dout, void* dqkv, const float* dsum, const float* tw_tab, const float* th_tab,
                   int batch, int heads, cudaStream_t stream) {
@@ -364,6 +750,18 @@ int attention_bwd_dkv_tc_launch(const void* qkv, const void* dout, void* dqkv, c
     if (head_dim == 80) return launch_dkv_tc<80>(qkv, dout, dqkv, dsum, tw_tab, th_tab, batch, heads, stream);
     if (head_dim == 64) return launch_dkv_tc<64>(qkv, dout, dqkv, dsum, tw_tab, th_tab, batch, heads, stream);
     return set_error(CVLM_ERR_UNSUPPORTED, "attention_bwd_dkv_tc: head_dim %d", head_dim);
+}
+
+// dQ columns of dqkv and D = rowsum(dO o) (into dsum) for the 64 x 64 global blocks, given the forward's tables.
+int attention_bwd_dq_tc_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* dsum, const float* tw_tab,
+                               const float* th_tab, const void* relh, const void* relw, int batch, int heads, int head_dim,
+                               cudaStream_t stream) {
+    if (batch > 65535) return set_error(CVLM_ERR_UNSUPPORTED, "attention_backward: batch exceeds grid.z; split the batch");
+    if ((reinterpret_cast<uintptr_t>(relh) & 15) || (reinterpret_cast<uintptr_t>(relw) & 15))
+        return set_error(CVLM_ERR_ARG, "attention_backward: rel-pos tables must be 16-byte aligned");
+    if (head_dim == 80) return launch_dq_tc<80>(qkv, o, dout, dqkv, dsum, tw_tab, th_tab, relh, relw, batch, heads, stream);
+    if (head_dim == 64) return launch_dq_tc<64>(qkv, o, dout, dqkv, dsum, tw_tab, th_tab, relh, relw, batch, heads, stream);
+    return set_error(CVLM_ERR_UNSUPPORTED, "attention_bwd_dq_tc: head_dim %d", head_dim);
 }
 
 }  // namespace cvlm

@@ -129,6 +129,9 @@ int attention_backward_launch(const void* qkv, const void* o, const void* dout, 
 // dK / dV of a 64 x 64 global block on tcgen05 (attention_bwd_tc.cu); dsum must hold D = rowsum(dO o) (the dQ kernel writes it)
 int attention_bwd_dkv_tc_launch(const void* qkv, const void* dout, void* dqkv, const float* dsum, const float* tw_tab,
                                 const float* th_tab, int batch, int heads, int head_dim, cudaStream_t stream);
+int attention_bwd_dq_tc_launch(const void* qkv, const void* o, const void* dout, void* dqkv, float* dsum, const float* tw_tab,
+                               const float* th_tab, const void* relh, const void* relw, int batch, int heads, int head_dim,
+                               cudaStream_t stream);
 int layernorm_train_launch(const float* x, const float* gamma, const float* beta, void* out_bf16, void* xhat_bf16,
                            float* rstd, long long rows, int cols, float eps, cudaStream_t stream);
 int ln_bwd_launch(int xhat_kind, const float* g, const float* gamma, const void* xsrc, const float* stat,

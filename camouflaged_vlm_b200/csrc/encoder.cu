@@ -56,7 +56,7 @@ static std::once_flag g_options_once;
 static void options_from_env() {
     for (int& v : g_options) v = 0;
     g_options[OPT_ATTN_POLY] = 4;
-    g_options[OPT_BWD_TC] = 1;            // dK / dV of the global blocks on the tcgen05 kernel when the forward left its tables
+    g_options[OPT_BWD_TC] = 2;            // backward of the global blocks on the tcgen05 kernels when the forward left its tables
     if (const char* e = getenv("CVLM_GEMM_MODE")) g_options[OPT_GEMM_MODE] = e[0] == '1' ? 1 : e[0] == 'p' ? 2 : 0;
     if (const char* e = getenv("CVLM_DEC_CLUSTER")) g_options[OPT_DEC_CLUSTER] = atoi(e);
     if (const char* e = getenv("CVLM_ATTN_LEGACY")) g_options[OPT_ATTN_LEGACY] = e[0] == '1';

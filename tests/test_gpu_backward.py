@@ -122,14 +122,17 @@ def test_attention_backward_with_the_forward_log_sum_exp(batch, grid, window, he
         # (the T_w table carries the row's log-sum-exp: tw = T_w - lse, so that P = exp2(s * scale + tw + th))
         assert _rel(tw.reshape(batch, grid, grid, heads, 64) + lse.reshape(batch, grid, grid, heads, 1), want_tw) < 1e-5
         assert _rel(th.reshape(batch, grid, grid, heads, 64), want_th) < 1e-5
-        for tc in (0, 1):       # mma.sync kernel with the tables (double-buffered) / tcgen05 kernel (attention_bwd_tc.cu)
+        # bwd_tc: 0 = mma.sync kernels with the tables, 1 = dK / dV on tcgen05, 2 = dQ too (attention_bwd_tc.cu; the default)
+        for tc in (0, 1, 2):
             _lib.set_option("bwd_tc", tc)
             try:
                 got_t = ops.attention_backward(qkv, o, dout, relh, relw, batch, grid, window, heads, hd, lse=lse, tables=(tw, th))
                 torch.cuda.synchronize()
             finally:
-                _lib.set_option("bwd_tc", 1)
-            assert torch.equal(got_t[:, :D], got[:, :D])             # dQ: same kernel
+                _lib.set_option("bwd_tc", 2)
+            if tc < 2:
+                assert torch.equal(got_t[:, :D], got[:, :D])         # dQ: same kernel
+            assert _rel(got_t[:, :D], dqkv0[:, :D]) < 3e-3, f"dQ, bwd_tc={tc}"
             assert _rel(got_t[:, D:2 * D], dqkv0[:, D:2 * D]) < 3e-3, f"dK, bwd_tc={tc}"
             assert _rel(got_t[:, 2 * D:], dqkv0[:, 2 * D:]) < 3e-3, f"dV, bwd_tc={tc}"
         got = got_t
