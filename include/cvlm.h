@@ -46,6 +46,8 @@ int cvlm_abi_version(void);
  *   "attn_legacy"  1 forces the mma.sync attention kernel (A/B runs)
  *   "attn_poly"    how many of every 16 exponential pairs of the global attention run on the FMA pipe (0,2,4,6,8)
  *   "win_mode"     window-attention kernel generation (0 = default)
+ *   "bwd_tc"       training, backward of the 64 x 64 global-attention blocks: 0 = mma.sync kernels, 1 = dK / dV on the
+ *                  tcgen05 kernel, 2 = dQ as well (default; needs the tables the training forward leaves)
  * No reference analogue (the reference has no native layer on this path). */
 int cvlm_set_option(const char* name, int value);
 int cvlm_get_option(const char* name, int* value);
